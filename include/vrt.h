@@ -1,0 +1,215 @@
+/*
+ * vrt.h — C ABI of libvrt.so, the B200-native (sm_100a) short-characteristics formal solver and
+ * Lambda-iteration engine for VoronoiRT's irregular-grid path.
+ *
+ * Every entry point replaces one Julia function of the reference (cited as file:line into the
+ * reference tree).  The reference has no FFI of its own: its boundary is the set of Julia functions
+ * the entry scripts call (compare_searchlight.jl, compare_continuum.jl, compare_line.jl); the Julia
+ * host `ccall`s these symbols through julia/VoronoiRTB200.jl.
+ *
+ * Conventions
+ *  - plain C types only; all array arguments are caller-owned.  Every array pointer may be a HOST
+ *    pointer or a CUDA DEVICE pointer: the library asks the driver (cudaPointerGetAttributes) and
+ *    copies as needed.  Host pointers are never retained after the call returns.
+ *  - array layouts are exactly what the Julia arrays hold (column-major): positions 3 x n with rows
+ *    (z,x,y); neighbours n x ld with column 0 = count, then 1-based ids, walls -5 (z_min) / -6
+ *    (z_max); S, J, alpha, damping nlam x n (wavelength fastest); populations n x 3; R, C 3 x 3 x n.
+ *  - ids and permutations are 1-based int64 at the ABI (what Julia holds).
+ *  - units are what `ustrip` yields in the reference: m, m^-1, kW m^-2 nm^-1, K, m^-3, m s^-1, nm, s^-1.
+ *  - every function returns 0 (VRT_OK) or a negative VRT_E_* code; vrt_last_error() gives the
+ *    thread-local message.  No exception crosses the boundary.  There is NO CPU fallback: without a
+ *    usable CUDA device every compute entry point returns VRT_E_CUDA.
+ */
+#ifndef VRT_H
+#define VRT_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VRT_ABI_VERSION 1
+
+enum {
+    VRT_OK = 0,
+    VRT_E_INVALID = -1,     /* bad argument */
+    VRT_E_CUDA = -2,        /* CUDA runtime/driver error, or no device */
+    VRT_E_NOMEM = -3,       /* host or device allocation failed */
+    VRT_E_GRID = -4,        /* neighbour graph not connected to the wall (the reference would loop forever) */
+    VRT_E_STATE = -5,       /* call order / handle state */
+    VRT_E_IO = -6           /* file parsing */
+};
+
+typedef struct vrt_grid vrt_grid;       /* replaces VoronoiSites' grid part (voronoi_utils.jl:7-28)   */
+typedef struct vrt_solver vrt_solver;   /* state of Λ_voronoi (lambda_iteration.jl:207, lambda_continuum.jl:109) */
+
+/* Two-level + continuum hydrogenic atom: the scalar fields of HydrogenicLine (line.jl:14-72) plus the
+ * three broadening constants γ_constant evaluates once per call (broadening.jl:63-82).
+ * γ_i = c_unsold*T^0.3*n_HI + gamma_natural + c_linear_stark*n_e^(2/3) + c_quadratic_stark*T^(1/6)*n_e
+ * with n_HI, n_e in m^-3 (the host folds Transparency.jl's unit factors into the constants). */
+typedef struct vrt_line {
+    int64_t nlam;            /* total number of wavelengths, λ = vcat(λbb, λbf_l, λbf_u) (line.jl:59) */
+    int64_t lidx[4];         /* line.λidx = [0, nbb, nbb+nbf, nbb+2nbf] (line.jl:61)                  */
+    double lambda0;          /* nm                                                                     */
+    double Aji, Bji, Bij;    /* s^-1, m^3 J^-1, m^3 J^-1 (line.jl:63-65)                               */
+    double chi_i, chi_j, chi_inf;  /* J                                                                */
+    int64_t gi, gj, Z;
+    double atom_weight;      /* kg */
+    double c_unsold;         /* const_unsold(line)           (broadening.jl:24-35)  */
+    double gamma_natural;    /* 4.702e8 s^-1                 (broadening.jl:76)     */
+    double c_linear_stark;   /* γ_linear_stark = c*n_e[m^-3]^(2/3)  (broadening.jl:77) */
+    double c_quadratic_stark;/* const_quadratic_stark(line)  (broadening.jl:52-61)  */
+} vrt_line;
+
+/* Per-site inputs, all length n unless noted.  The one-time Transparency.jl quantities (α_cont, C, ε,
+ * LTE populations, ΔD) are computed by the host exactly as Λ_voronoi does before its loop
+ * (lambda_iteration.jl:216-247) and passed in. */
+typedef struct vrt_site_data {
+    const double* temperature;        /* K      */
+    const double* electron_density;   /* m^-3   */
+    const double* hydrogen_density;   /* m^-3, sites.hydrogen_populations (N_H) */
+    const double* velocity_z;         /* m/s    */
+    const double* velocity_x;
+    const double* velocity_y;
+    const double* doppler_width;      /* line.ΔD, nm (line.jl:67) */
+    const double* alpha_cont;         /* m^-1  (lambda_iteration.jl:223-230) */
+    const double* destruction;        /* ελ    (lambda_iteration.jl:244)     */
+    const double* C;                  /* 3 x 3 x n collisional rates, s^-1 (rates.jl:52-85) */
+    const double* lte_pops;           /* n x 3 LTE populations, m^-3 (populations.jl:112-138) */
+} vrt_site_data;
+
+/* Angular quadrature table: the three columns of quadratures/*.dat (functions.jl:33-63), degrees. */
+typedef struct vrt_quadrature {
+    int64_t n_dirs;
+    const double* weights;
+    const double* theta;
+    const double* phi;
+} vrt_quadrature;
+
+typedef struct vrt_config {
+    int32_t n_sweeps;        /* in-layer Gauss–Seidel sweeps; the reference hard-wires 3 (lambda_iteration.jl:82) */
+    int32_t reserved0;
+    double p;                /* upwind weighting exponent, `const p = 7.0` (irregular_ray_tracing.jl:1) */
+    int64_t lam_begin;       /* wavelength shard [lam_begin, lam_end) owned by this process, 0-based;   */
+    int64_t lam_end;         /*   0,0 = all wavelengths                                                  */
+    int64_t lam_chunk;       /* wavelengths swept together per pass (0 = choose from free HBM)          */
+    int32_t prune;           /* 1 = skip re-sweeps of cells whose value cannot change (exact), 0 = visit every cell n_sweeps times */
+    int32_t tile_cells;      /* cells per work tile (0 = default)                                       */
+} vrt_config;
+
+/* all-reduce hook for the wavelength-sharded multi-GPU path: called with a DEVICE buffer of `count`
+ * doubles that must be reduced in place over all shards (op 0 = sum, 1 = max). */
+typedef int (*vrt_allreduce_fn)(void* dev_buf, int64_t count, int32_t op, void* user);
+
+/* per-iteration report handed to the host callback (replaces the println/HDF5 hooks at
+ * lambda_iteration.jl:245,280-281,315-317,346) */
+typedef struct vrt_iter_info {
+    int32_t iteration;       /* 1-based index of the iteration that just finished            */
+    int32_t reserved0;
+    double diff;             /* criterion value evaluated BEFORE this iteration (lambda_iteration.jl:325-349) */
+    double t_opacity_ms, t_sweep_ms, t_source_ms, t_rates_ms, t_stateq_ms, t_total_ms;
+    double updates;          /* n * n_dirs * nlam_local */
+} vrt_iter_info;
+typedef int (*vrt_iter_cb)(const vrt_iter_info* info, void* user);   /* nonzero return stops the loop */
+
+typedef struct vrt_result {
+    int32_t iterations;
+    int32_t converged;
+    double diff;             /* last criterion value */
+    double seconds;
+} vrt_result;
+
+/* ---------------------------------------------------------------- misc */
+int vrt_abi_version(void);
+const char* vrt_last_error(void);
+int vrt_device_count(int32_t* count);
+int vrt_set_device(int32_t device);
+
+/* ---------------------------------------------------------------- grid: read_cell (voronoi_utils.jl:36-85) */
+
+/* Parse the voro++ neighbour text file "id nb1 nb2 ..." (voronoi_utils.jl:42-70; written by
+ * rt_preprocessing/output_sites.cc:49).  Call once with nbr == NULL to get ld (= max neighbours + 1),
+ * then again with an n x ld int64 buffer (column-major, zero-filled by the library). */
+int vrt_read_neighbours(const char* fname, int64_t n, int64_t* nbr, int64_t ld, int64_t* ld_needed);
+
+/* Build the grid: layers from the bottom/top wall (_sort_by_layer_up/_down, voronoi_utils.jl:93-174),
+ * stable sort permutations and reduce_layers offsets (:71-79,:253-269), unit Delaunay edge vectors
+ * (calc_Delaunay_lines, :186-245).  bounds = {z_min,z_max,x_min,x_max,y_min,y_max}. */
+int vrt_grid_create(int64_t n, const double* positions, const int64_t* nbr, int64_t ld,
+                    const double bounds[6], vrt_grid** out);
+void vrt_grid_destroy(vrt_grid* g);
+int vrt_grid_size(const vrt_grid* g, int64_t* n, int64_t* max_nb);
+/* number of layers L (offsets has L+1 entries) */
+int vrt_grid_num_layers(const vrt_grid* g, int32_t down, int64_t* L);
+/* perm (n, 1-based site ids) and offsets (L+1, 1-based, reference semantics: last entry = n, voronoi_utils.jl:266) */
+int vrt_grid_get_layers(const vrt_grid* g, int32_t down, int64_t* perm, int64_t* offsets);
+/* Delaunay_lines 3 x max_nb x n (wall slots are written as 0; the reference leaves them undefined) */
+int vrt_grid_get_delaunay_lines(const vrt_grid* g, double* lines);
+
+/* Upwind stencil for direction k (smallest_angle, voronoi_utils.jl:360-396; weights
+ * irregular_ray_tracing.jl:51; path length :66), in host site order.  upwind 2 x n (1-based ids),
+ * dots/weights/r 2 x n.  Any output may be NULL. */
+int vrt_grid_get_stencil(vrt_grid* g, const double k[3], double p,
+                         int64_t* upwind, double* dots, double* weights, double* r);
+
+/* Sweep schedule for direction k: per site, host order:
+ *   cls 2 x n: class of each upwind reference (0 FINAL, 1 THIS, 2 LAG, 3 ZERO; -1 for unprocessed sites),
+ *   sublevel n: 1-based in-layer dependency level of sweep 1 (0 for boundary / unprocessed sites),
+ *   stab n: sweep after which the site's value no longer changes (1..n_sweeps; 0 boundary/unprocessed).
+ * n_steps = number of grid-wide dependent steps of the sweep program actually executed. */
+int vrt_grid_get_schedule(vrt_grid* g, const double k[3], int32_t down, int32_t n_sweeps, int32_t prune,
+                          int32_t* cls, int32_t* sublevel, int32_t* stab, int64_t* n_steps, int64_t* n_visits);
+
+/* ---------------------------------------------------------------- formal solver */
+
+/* Delaunay_upII (down=0) / Delaunay_downII (down=1) (irregular_ray_tracing.jl:15-82, :96-163), batched
+ * over nlam independent wavelengths: S, alpha, I_out are nlam x n; I0 is nlam x n1 in perm order
+ * (n1 = offsets[1]-1 boundary sites).  p is the exponent the stale 7-argument call sites pass
+ * (compare_searchlight.jl:309,429). */
+int vrt_formal_solve(vrt_grid* g, const double k[3], int32_t down, double p, int32_t n_sweeps,
+                     int64_t nlam, const double* S, const double* alpha, const double* I0, double* I_out);
+
+/* ---------------------------------------------------------------- Λ-iteration engine */
+
+/* NLTE line solver state (Λ_voronoi, lambda_iteration.jl:207-297). lambda: nlam wavelengths, nm. */
+int vrt_solver_create_line(vrt_grid* g, const vrt_line* line, const double* lambda,
+                           const vrt_site_data* sites, const vrt_quadrature* quad,
+                           const vrt_config* cfg, vrt_solver** out);
+/* 500 nm continuum solver state (Λ_voronoi, lambda_continuum.jl:109-160): alpha_cont, eps (ε_λ), B0 length n. */
+int vrt_solver_create_continuum(vrt_grid* g, const double* alpha_cont, const double* eps, const double* B0,
+                                const vrt_quadrature* quad, const vrt_config* cfg, vrt_solver** out);
+void vrt_solver_destroy(vrt_solver* s);
+int vrt_solver_set_allreduce(vrt_solver* s, vrt_allreduce_fn fn, void* user);
+/* local wavelength count of this shard */
+int vrt_solver_nlam_local(const vrt_solver* s, int64_t* nlam_local);
+
+/* J_λ_voronoi (lambda_iteration.jl:60-113 / lambda_continuum.jl:27-56).  S, J: nlam_local x n;
+ * populations n x 3 (NULL for the continuum solver); damping (optional) nlam_local x n. */
+int vrt_mean_intensity(vrt_solver* s, const double* S, const double* populations, double* J, double* damping);
+
+/* calculate_R (rates.jl:154-201): J nlam_local x n -> R 3 x 3 x n.  damping NULL = use the γ of the last
+ * vrt_mean_intensity call.  With a wavelength shard the result is this shard's partial sum unless an
+ * all-reduce hook is set. */
+int vrt_calculate_R(vrt_solver* s, const double* J, const double* damping, double* R);
+
+/* get_revised_populations (populations.jl:191-221): R, C 3 x 3 x n, N_H n -> populations n x 3. */
+int vrt_get_revised_populations(int64_t n, const double* R, const double* C, const double* N_H, double* populations);
+
+/* Λ_voronoi loop (lambda_iteration.jl:253-285 / lambda_continuum.jl:145-149).  Starts from S = B_0 and
+ * LTE populations unless vrt_set_state was called. */
+int vrt_lambda_iterate(vrt_solver* s, double eps, int32_t maxiter, vrt_iter_cb cb, void* user, vrt_result* out);
+
+/* checkpoint hooks (replace write_to_file / recover_simulation.jl): any pointer may be NULL.
+ * S, J nlam_local x n; populations n x 3. */
+int vrt_get_state(vrt_solver* s, double* S, double* J, double* populations);
+int vrt_set_state(vrt_solver* s, const double* S, const double* populations);
+
+/* counters of the last vrt_mean_intensity / vrt_formal_solve call on this thread's device:
+ * out[0] kernels launched, out[1] cell visits, out[2] dependent steps, out[3] sweep-kernel ms (CUDA events) */
+int vrt_last_stats(double out[8]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VRT_H */
