@@ -79,7 +79,7 @@ typedef struct vrt_site_data {
     const double* lte_pops;           /* n x 3 LTE populations, m^-3 (populations.jl:112-138) */
 } vrt_site_data;
 
-/* Angular quadrature table: the three columns of quadratures/*.dat (functions.jl:33-63), degrees. */
+/* Angular quadrature table: the three columns of the quadratures .dat files (functions.jl:33-63), degrees. */
 typedef struct vrt_quadrature {
     int64_t n_dirs;
     const double* weights;
@@ -181,6 +181,11 @@ int vrt_solver_create_continuum(vrt_grid* g, const double* alpha_cont, const dou
                                 const vrt_quadrature* quad, const vrt_config* cfg, vrt_solver** out);
 void vrt_solver_destroy(vrt_solver* s);
 int vrt_solver_set_allreduce(vrt_solver* s, vrt_allreduce_fn fn, void* user);
+/* (Re)upload one per-site input of the line solver.  In the reference these are plain function arguments
+ * (α_cont of J_λ_voronoi, LTE_pops of calculate_R, C of get_revised_populations), so a drop-in caller may
+ * hand them over late or change them between calls.  Shapes as in vrt_site_data. */
+enum { VRT_FIELD_ALPHA_CONT = 0, VRT_FIELD_DESTRUCTION = 1, VRT_FIELD_C = 2, VRT_FIELD_LTE_POPS = 3 };
+int vrt_solver_set_field(vrt_solver* s, int32_t field, const double* data);
 /* local wavelength count of this shard */
 int vrt_solver_nlam_local(const vrt_solver* s, int64_t* nlam_local);
 

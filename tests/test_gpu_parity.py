@@ -1,0 +1,383 @@
+"""Parity of the CUDA path (through the C ABI, via the host mirror voronoirt_b200.api) against the CPU oracle
+on the committed fixtures.  Tolerances: integers bit-exact; fp64 intensities and J 1e-9 relative
+(BASELINE.json north_star); populations 1e-6 relative.  Run on the B200 box: pytest -m gpu."""
+import numpy as np
+import pytest
+
+from conftest import load_grid, oracle_sites
+
+pytestmark = pytest.mark.gpu
+
+UL7N12 = None
+
+
+def rel_err(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    scale = np.maximum(np.abs(b).max(), 1e-300)
+    return np.abs(a - b).max() / scale
+
+
+def pointwise_rel(a, b, floor):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return (np.abs(a - b) / np.maximum(np.abs(b), floor)).max()
+
+
+@pytest.fixture(scope="module")
+def V():
+    import voronoirt_b200 as V
+    from voronoirt_b200 import _lib
+    import ctypes as C
+    cnt = C.c_int32()
+    _lib.check(_lib.lib().vrt_device_count(C.byref(cnt)))
+    assert cnt.value >= 1, "no CUDA device: the product has no CPU fallback"
+    return V
+
+
+def quad(V, name):
+    return V.read_quadrature(V.quadrature_path(name))
+
+
+def make(V, O, name):
+    pos, nbr, b = load_grid(name)
+    n = pos.shape[1]
+    cell = V.read_cell(nbr, n, pos, b[2], b[3], b[4], b[5])
+    rng = np.random.default_rng(11)
+    sites = V.VoronoiSites(*cell, np.ones(n), np.zeros(n), np.zeros(n), np.zeros(n), np.zeros(n), np.zeros(n),
+                           b[0], b[1], b[2], b[3], b[4], b[5], n)
+    return sites, oracle_sites(O, pos, nbr, b), pos, nbr, b, rng
+
+
+GRIDS = ["grid_unit1000", "grid_strat3000", "grid_unit300"]
+
+
+@pytest.mark.parametrize("name", GRIDS)
+def test_layers_and_perms_bit_exact(V, oracle, name):
+    sites, osites, *_ = make(V, oracle, name)
+    for down, perm, off in ((0, sites.perm_up, sites.layers_up), (1, sites.perm_down, sites.layers_down)):
+        operm, ooff = osites.layers(down)
+        assert np.array_equal(perm, operm)
+        assert np.array_equal(off, ooff)
+        assert off[-1] == sites.n  # reduce_layers stores n, not n+1 (Q1)
+
+
+@pytest.mark.parametrize("name", GRIDS)
+def test_delaunay_lines_and_stencil(V, oracle, name):
+    sites, osites, pos, nbr, b, rng = make(V, oracle, name)
+    lines = sites._grid.delaunay_lines()           # (3, max_nb, n)
+    olines = osites.delaunay_lines()               # (n, max_nb, 3)
+    assert np.array_equal(np.ascontiguousarray(lines.T), olines)  # bit-exact: same rounded operations
+    w, th, ph, nq = quad(V, "ul9n20")
+    for i in range(nq):
+        k = V.direction(th[i], ph[i])
+        up, dots, wts, r = sites._grid.stencil(k)
+        oup, odots, ow, orr = osites.stencil(k)
+        assert np.array_equal(up.T, oup), f"stencil ids differ for direction {i}"
+        assert np.array_equal(dots.T, odots)
+        assert np.array_equal(r.T, orr)
+        assert pointwise_rel(wts.T, ow, 1e-300) < 1e-14
+
+
+def seq_schedule(osites, up, down):
+    """sequential recomputation of reference classes and sub-levels for one direction"""
+    perm, off = osites.layers(down)
+    n = len(perm)
+    L = len(off) - 1
+    layer = np.zeros(n, dtype=np.int64)
+    rank = np.zeros(n, dtype=np.int64)
+    for l in range(L):
+        lo, hi = off[l] - 1, (off[l + 1] - 1 if l + 1 < L else n)
+        layer[perm[lo:hi] - 1] = l + 1
+    rank[perm - 1] = np.arange(n)
+    X = perm[-1] - 1
+    cls = -np.ones((n, 2), dtype=np.int64)
+    sub = np.zeros(n, dtype=np.int64)
+    for l in range(2, L + 1):
+        lo, hi = off[l - 1] - 1, (off[l] - 1)
+        order = range(lo, hi) if not down else range(hi - 1, lo - 1, -1)
+        done = set()
+        for r in order:
+            c = perm[r] - 1
+            if c == X:
+                continue
+            s = 1
+            for m in range(2):
+                u = up[c, m] - 1
+                if u == X:
+                    k = 3
+                elif layer[u] < l:
+                    k = 0
+                elif layer[u] > l:
+                    k = 3
+                elif u in done:
+                    k = 1
+                    s = max(s, sub[u] + 1)
+                else:
+                    k = 2
+                cls[c, m] = k
+            sub[c] = s
+            done.add(c)
+    return cls, sub
+
+
+@pytest.mark.parametrize("name", ["grid_unit1000", "grid_strat3000"])
+def test_schedule_classes_and_sublevels(V, oracle, name):
+    sites, osites, *_ = make(V, oracle, name)
+    w, th, ph, nq = quad(V, "ul7n12")
+    for i in (0, 1, 2, 3, 8, 9):
+        k = V.direction(th[i], ph[i])
+        down = int(not th[i] > 90)
+        oup, *_ = osites.stencil(k)
+        ecls, esub = seq_schedule(osites, oup, down)
+        for prune in (0, 1):
+            cls, sub, stab, nsteps, nvis = sites._grid.schedule(k, down, 3, prune)
+            assert np.array_equal(cls.T, ecls)
+            assert np.array_equal(sub, esub)
+            processed = esub > 0
+            if prune == 0:
+                assert np.all(stab[processed] == 3) and nvis == 3 * processed.sum()
+            else:
+                assert np.all((stab[processed] >= 1) & (stab[processed] <= 3)) and nvis == stab.sum()
+            assert np.all(stab[~processed] == 0)
+
+
+def fields(pos, rng, nlam, kind):
+    n = pos.shape[1]
+    if kind == "smooth":
+        S = (1 + pos[0] / np.abs(pos[0]).max())[None, :] * (1 + 0.1 * np.arange(nlam))[:, None]
+        z = (pos[1] - pos[1].min()) / (pos[1].max() - pos[1].min())
+        box = pos[0].max() - pos[0].min()
+        alpha = (5 * (1 + z))[None, :] / box * (1 + np.arange(nlam))[:, None] ** 1.5
+    elif kind == "random":
+        S = rng.random((nlam, n)) + 0.1
+        box = pos[0].max() - pos[0].min()
+        alpha = 10 ** rng.uniform(-4, 3, size=(nlam, n)) / box   # Δτ from the Taylor branch to the >50 branch (Q7)
+    else:  # searchlight: α = 0, S = 0 (compare_searchlight.jl:64-65)
+        S = np.zeros((nlam, n))
+        alpha = np.zeros((nlam, n))
+    return np.asfortranarray(S), np.asfortranarray(alpha)
+
+
+@pytest.mark.parametrize("name,nlam,kind", [("grid_unit1000", 1, "smooth"), ("grid_unit1000", 3, "random"),
+                                            ("grid_strat3000", 12, "random"), ("grid_strat3000", 91, "smooth"),
+                                            ("grid_unit300", 5, "searchlight"), ("grid_unit300", 33, "random")])
+def test_formal_solve_matches_oracle(V, oracle, name, nlam, kind):
+    sites, osites, pos, nbr, b, rng = make(V, oracle, name)
+    S, alpha = fields(pos, rng, nlam, kind)
+    w, th, ph, nq = quad(V, "ul7n12")
+    worst = 0.0
+    for i in range(nq):
+        k = V.direction(th[i], ph[i])
+        down = int(not th[i] > 90)
+        n1 = (sites.layers_down if down else sites.layers_up)[1] - 1
+        I0 = np.asfortranarray(rng.random((nlam, n1)) + 0.5) if kind != "smooth" else np.full((nlam, n1), 0.0 if down else 2.0, order="F")
+        fn = V.Delaunay_downII if down else V.Delaunay_upII
+        I = fn(k, S, I0, alpha, sites, 3)
+        Iref = osites.formal_solve(k, down, S.T, alpha.T, I0.T, n_sweeps=3, hoist=0)   # faithful: stencil per visit
+        err = rel_err(I.T, Iref)
+        worst = max(worst, err)
+        assert err < 1e-9, f"direction {i}: {err}"
+        # the never-processed last-rank site keeps I = 0 (Q1)
+        last = (sites.perm_down if down else sites.perm_up)[-1] - 1
+        assert np.all(I[:, last] == 0)
+    print("worst rel err", worst)
+
+
+def test_formal_solve_vector_form_and_sweep_counts(V, oracle):
+    """1-D (single wavelength) call form of the reference + n_sweeps other than 3 + the p=50 variant (Q11)"""
+    sites, osites, pos, nbr, b, rng = make(V, oracle, "grid_unit1000")
+    n = sites.n
+    S = 1 + pos[0]
+    alpha = 5 * (1 + pos[1])
+    k = V.direction(152.666292044518485, 315.475247829748128)
+    I0 = np.full(sites.layers_up[1] - 1, 2.0)
+    I = V.Delaunay_upII(k, S, I0, alpha, sites, 3)
+    # SURVEY App. F known answers for this exact input
+    assert abs(I.sum() - 1555.62395847965) < 1e-8
+    assert abs(I[499] - 1.32166712111356) < 1e-12 and abs(I[999] - 1.27975253140188) < 1e-12 and I[977] == 0.0
+    for ns, p in ((1, 7.0), (2, 7.0), (4, 7.0), (3, 50.0), (3, 1.0)):
+        I = V.Delaunay_upII(k, S, I0, alpha, sites, ns, p)
+        Iref = osites.formal_solve(k, 0, S, alpha, I0, n_sweeps=ns, p=p, hoist=0)[:, 0]
+        assert rel_err(I, Iref) < 1e-9
+    kd = V.direction(27.333707955481518, 135.475247829748128)
+    I = V.Delaunay_downII(kd, S, np.zeros(sites.layers_down[1] - 1), alpha, sites, 3)
+    assert abs(I.sum() - 1267.91998391497) < 1e-8 and I[988] == 0.0
+
+
+def line_problem(V, O, name, nbb=50, nbf=20):
+    from voronoirt_b200 import synth
+    pos, nbr, b = load_grid(name)
+    n = pos.shape[1]
+    if name.startswith("grid_unit"):   # map the unit box onto the synthetic atmosphere box
+        B = synth.BOX
+        a = synth.atmosphere(B["z_min"] + pos[0] * (B["z_max"] - B["z_min"]), pos[1] * B["x_max"], pos[2] * B["y_max"])
+        scale = 2.0e5
+        pos = np.asfortranarray(pos * scale)
+        b = b * scale
+    else:
+        a = synth.atmosphere(pos[0], pos[1], pos[2])
+    cell = V.read_cell(nbr, n, pos, b[2], b[3], b[4], b[5])
+    sites = V.VoronoiSites(*cell, a["temperature"], a["electron_density"], a["hydrogen_density"], a["velocity_z"],
+                           a["velocity_x"], a["velocity_y"], b[0], b[1], b[2], b[3], b[4], b[5], n)
+    line, lte, α_cont, ελ, Cr = synth.line_inputs(a["temperature"], a["electron_density"], a["hydrogen_density"], nbb, nbf)
+    osites = oracle_sites(O, pos, nbr, b)
+    sd = O.make_site_data(temperature=a["temperature"], electron_density=a["electron_density"], hydrogen_density=a["hydrogen_density"],
+                          velocity_z=a["velocity_z"], velocity_x=a["velocity_x"], velocity_y=a["velocity_y"], doppler_width=line.ΔD,
+                          alpha_cont=α_cont, destruction=ελ, C=np.ascontiguousarray(Cr.T), lte_pops=np.ascontiguousarray(lte.T))
+    return dict(sites=sites, osites=osites, line=line, lte=lte, α_cont=α_cont, ελ=ελ, C=Cr, sd=sd, atm=a, n=n)
+
+
+@pytest.mark.parametrize("name,qname", [("grid_unit1000", "ul7n12"), ("grid_strat3000", "ul9n20")])
+def test_J_lambda_voronoi_line(V, oracle, name, qname):
+    from voronoirt_b200 import atom
+    P = line_problem(V, oracle, name)
+    line, sites = P["line"], P["sites"]
+    qp = V.quadrature_path(qname)
+    w, th, ph, nq = V.read_quadrature(qp)
+    S = np.asfortranarray(atom.B_λ(line.λ[:, None], sites.temperature[None, :]))
+    J, damping = V.J_λ_voronoi(S, P["α_cont"], P["lte"], sites, line, qp)
+    oq = oracle.make_quadrature(w, th, ph)
+    Jref, dref = oracle.J_lambda_voronoi(P["osites"], line.as_struct(), line.λ, P["sd"], oq, S.T, P["lte"].T, hoist=1)
+    assert pointwise_rel(damping.T, dref, 1e-300) < 1e-12
+    assert rel_err(J.T, Jref) < 1e-9
+    # per-wavelength check as well (each wavelength against its own scale)
+    for l in range(J.shape[0]):
+        assert rel_err(J[l], Jref[:, l]) < 1e-9, l
+    # rates and statistical equilibrium on top of it
+    R = V.calculate_R(sites, line, J, damping, P["lte"], qp)
+    Rref = oracle.calculate_R(line.as_struct(), line.λ, sites.temperature, line.ΔD, Jref, dref, P["lte"].T)
+    Rt = np.ascontiguousarray(R.T)   # (n, 3, 3) with [i, b, a]
+    for (a_, b_) in ((0, 1), (1, 0), (0, 2), (2, 0), (1, 2), (2, 1)):
+        assert pointwise_rel(Rt[:, b_, a_], Rref[:, b_, a_], 1e-300) < 1e-9, (a_, b_)
+    assert np.all(Rt[:, 0, 0] == 0) and np.all(Rt[:, 1, 1] == 0) and np.all(Rt[:, 2, 2] == 0)
+    pops = V.get_revised_populations(R, P["C"], sites.hydrogen_populations)
+    pref = oracle.get_revised_populations(Rref, np.ascontiguousarray(P["C"].T), sites.hydrogen_populations)
+    assert pointwise_rel(pops.T, pref, 1e-300) < 1e-6
+    assert pointwise_rel(pops.sum(axis=1), sites.hydrogen_populations, 1e-300) < 1e-12   # n1+n2+n3 = N_H
+
+
+def test_lambda_iteration_line(V, oracle):
+    from voronoirt_b200 import atom
+    P = line_problem(V, oracle, "grid_unit1000", nbb=10, nbf=4)
+    line, sites = P["line"], P["sites"]
+    qp = V.quadrature_path("ul2n3")
+    w, th, ph, nq = V.read_quadrature(qp)
+    maxiter = 4
+    J, S, α_cont, pops = V.Λ_voronoi(1e-3, maxiter, sites, line, qp, None, α_cont=P["α_cont"], ελ=P["ελ"], C=P["C"], LTE_pops=P["lte"])
+    res = V.Λ_voronoi.last
+    S0 = atom.B_λ(line.λ[:, None], sites.temperature[None, :]).T
+    oq = oracle.make_quadrature(w, th, ph)
+    Jr, Sr, pr, conv, it = oracle.lambda_voronoi(P["osites"], line.as_struct(), line.λ, P["sd"], oq, S0, P["lte"].T, eps=1e-3, maxiter=maxiter)
+    assert res["iterations"] == it
+    assert rel_err(S.T, Sr) < 1e-9 and rel_err(J.T, Jr) < 1e-9
+    assert pointwise_rel(pops.T, pr, 1e-300) < 1e-6
+    diffs = [h["diff"] for h in res["history"]] + [res["diff"]]
+    assert np.allclose(diffs, conv[:len(diffs)], rtol=1e-9)
+    assert diffs[0] == 1.0   # first pass: S_old = 0
+
+
+def test_lambda_iteration_continuum(V, oracle):
+    from voronoirt_b200 import synth
+    pos, nbr, b = load_grid("grid_strat3000")
+    n = pos.shape[1]
+    a = synth.atmosphere(pos[0], pos[1], pos[2])
+    cell = V.read_cell(nbr, n, pos, b[2], b[3], b[4], b[5])
+    sites = V.VoronoiSites(*cell, a["temperature"], a["electron_density"], a["hydrogen_density"], a["velocity_z"],
+                           a["velocity_x"], a["velocity_y"], b[0], b[1], b[2], b[3], b[4], b[5], n)
+    α_cont, ε, B0 = synth.continuum_inputs(a["temperature"], a["electron_density"], a["hydrogen_density"])
+    qp = V.quadrature_path("ul7n12")
+    w, th, ph, nq = V.read_quadrature(qp)
+    osites = oracle_sites(oracle, pos, nbr, b)
+    oq = oracle.make_quadrature(w, th, ph)
+    # one formal solution: J_λ_voronoi(S, α_cont, sites, quadrature) (lambda_continuum.jl:27)
+    from voronoirt_b200 import atom
+    J1 = V.J_λ_voronoi(B0, α_cont, sites, qp)
+    J1ref = oracle.J_continuum(osites, oq, B0, α_cont, atom.B_λ(500.0, sites.temperature))
+    assert rel_err(J1, J1ref) < 1e-9
+    J, S, _ = V.Λ_voronoi(1e-3, 6, sites, qp, α_cont=α_cont, ε_λ=ε, B_0=B0)
+    res = V.Λ_voronoi.last
+    Jr, Sr, conv, it = oracle.lambda_continuum(osites, oq, α_cont, ε, B0, eps=1e-3, maxiter=6)
+    assert res["iterations"] == it
+    assert rel_err(S, Sr) < 1e-9 and rel_err(J, Jr) < 1e-9
+
+
+def test_wavelength_shards_sum_to_full_rates(V, oracle):
+    """two wavelength shards in one process: partial rates add up to the unsharded rates; J slices agree bit for bit"""
+    from voronoirt_b200 import atom
+    P = line_problem(V, oracle, "grid_unit300", nbb=10, nbf=4)
+    line, sites = P["line"], P["sites"]
+    qp = V.quadrature_path("ul2n3")
+    nl = len(line.λ)
+    S = np.asfortranarray(atom.B_λ(line.λ[:, None], sites.temperature[None, :]))
+    full = V.Solver(sites, qp, line=line, α_cont=P["α_cont"], ελ=P["ελ"], C_rates=P["C"], LTE_pops=P["lte"])
+    Jf = full.mean_intensity(S, P["lte"])
+    Rf = full.calculate_R(Jf)
+    Rsum = np.zeros_like(Rf)
+    for lo, hi in ((0, nl // 2), (nl // 2, nl)):
+        sh = V.Solver(sites, qp, line=line, α_cont=P["α_cont"], ελ=P["ελ"], C_rates=P["C"], LTE_pops=P["lte"], lam_range=(lo, hi))
+        Js = sh.mean_intensity(np.asfortranarray(S[lo:hi]), P["lte"])
+        assert np.array_equal(Js, Jf[lo:hi])
+        Rsum += sh.calculate_R(Js)
+        sh.close()
+    full.close()
+    nz = Rf != 0
+    assert pointwise_rel(Rsum[nz], Rf[nz], 1e-300) < 1e-12
+
+
+def test_lambda_chunking_and_direction_batches_do_not_change_J(V, oracle, monkeypatch):
+    from voronoirt_b200 import atom
+    P = line_problem(V, oracle, "grid_unit300", nbb=10, nbf=4)
+    line, sites = P["line"], P["sites"]
+    qp = V.quadrature_path("ul7n12")
+    S = np.asfortranarray(atom.B_λ(line.λ[:, None], sites.temperature[None, :]))
+    a = V.Solver(sites, qp, line=line, α_cont=P["α_cont"], LTE_pops=P["lte"])
+    Ja = a.mean_intensity(S, P["lte"])
+    a.close()
+    monkeypatch.setenv("VRT_MAX_DIRS", "5")
+    b = V.Solver(sites, qp, line=line, α_cont=P["α_cont"], LTE_pops=P["lte"], lam_chunk=7)
+    Jb = b.mean_intensity(S, P["lte"])
+    b.close()
+    assert np.array_equal(Ja, Jb)   # same operations in the same order: bit-identical
+    c = V.Solver(sites, qp, line=line, α_cont=P["α_cont"], LTE_pops=P["lte"], prune=0)
+    Jc = c.mean_intensity(S, P["lte"])
+    c.close()
+    assert np.array_equal(Ja, Jc)   # pruning skips only re-evaluations that reproduce the same value
+
+
+def test_device_pointers_and_determinism(V, oracle):
+    """inputs/outputs resident in HBM (torch CUDA tensors) give the same bits as host buffers; reruns are bit-identical"""
+    import torch
+    sites, osites, pos, nbr, b, rng = make(V, oracle, "grid_strat3000")
+    nlam = 16
+    S, alpha = fields(pos, rng, nlam, "random")
+    k = V.direction(109.707418891553175, 193.587044948382584)
+    n1 = sites.layers_up[1] - 1
+    I0 = np.asfortranarray(rng.random((nlam, n1)))
+    I_host = V.Delaunay_upII(k, S, I0, alpha, sites, 3)
+    I_host2 = V.Delaunay_upII(k, S, I0, alpha, sites, 3)
+    assert np.array_equal(I_host, I_host2)
+    from voronoirt_b200 import _lib
+    import ctypes as C
+    dS = torch.from_numpy(np.ascontiguousarray(S.T)).cuda()       # (n, nlam) C-order == (nlam, n) Fortran
+    dA = torch.from_numpy(np.ascontiguousarray(alpha.T)).cuda()
+    dI0 = torch.from_numpy(np.ascontiguousarray(I0.T)).cuda()
+    dI = torch.zeros_like(dS)
+    kk = np.ascontiguousarray(k)
+    _lib.check(_lib.lib().vrt_formal_solve(sites._grid.h, C.c_void_p(kk.ctypes.data), 0, 7.0, 3, nlam, C.c_void_p(dS.data_ptr()),
+                                           C.c_void_p(dA.data_ptr()), C.c_void_p(dI0.data_ptr()), C.c_void_p(dI.data_ptr())))
+    torch.cuda.synchronize()
+    assert np.array_equal(dI.cpu().numpy().T, I_host)
+
+
+def test_errors_are_reported_not_raised_across_the_abi(V):
+    from voronoirt_b200 import _lib
+    import ctypes as C
+    L = _lib.lib()
+    h = C.c_void_p()
+    assert L.vrt_grid_create(0, None, None, 0, None, C.byref(h)) == -1 and L.vrt_last_error()
+    # a site that no wall can reach: the reference would spin forever in _sort_by_layer_up; we return VRT_E_GRID
+    pos = np.asfortranarray(np.random.default_rng(0).random((3, 4)))
+    nbr = np.asfortranarray(np.array([[2, 2, -5], [2, 1, -6], [1, 4, 0], [1, 3, 0]], dtype=np.int64))
+    b = np.array([0, 1, 0, 1, 0, 1.0])
+    rc = L.vrt_grid_create(4, C.c_void_p(pos.ctypes.data), C.c_void_p(nbr.ctypes.data), 3, C.c_void_p(b.ctypes.data), C.byref(h))
+    assert rc == -4
+    assert b"not connected" in L.vrt_last_error()

@@ -86,6 +86,7 @@ PROTOTYPES = {
                                               C.POINTER(vrt_config), C.POINTER(C.c_void_p)]),
     "vrt_solver_destroy": (None, [C.c_void_p]),
     "vrt_solver_set_allreduce": (C.c_int, [C.c_void_p, vrt_allreduce_fn, C.c_void_p]),
+    "vrt_solver_set_field": (C.c_int, [C.c_void_p, C.c_int32, P]),
     "vrt_solver_nlam_local": (C.c_int, [C.c_void_p, c_int64_p]),
     "vrt_mean_intensity": (C.c_int, [C.c_void_p, P, P, P, P]),
     "vrt_calculate_R": (C.c_int, [C.c_void_p, P, P, P]),

@@ -1,0 +1,446 @@
+"""Host-side mirror of the reference's Julia interface for the irregular-grid path.
+
+Same names, argument order and meaning as the functions the entry scripts call
+(compare_searchlight.jl, compare_continuum.jl, compare_line.jl), implemented as thin calls into the
+C ABI of libvrt.so (include/vrt.h).  Arrays use the reference's logical shapes in Fortran order, i.e.
+exactly the memory layout of the Julia arrays: positions (3, n) rows (z, x, y); NeighbourMatrix
+(n, ld); S_λ, J_λ, α, damping (nλ, n); populations (n, 3); R, C (3, 3, n).  Ids are 1-based.
+All compute happens on the GPU; there is no CPU path in this module.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from . import _abi
+from ._lib import check, lib, last_stats  # noqa: F401
+from .atom import HydrogenicLine  # noqa: F401
+
+
+def _f(a, dtype=np.float64):
+    return np.asfortranarray(a, dtype=dtype)
+
+
+def _ptr(a):
+    """address of a numpy array, a torch CUDA tensor, or a raw int device pointer (None -> NULL)"""
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return C.c_void_p(a)
+    if hasattr(a, "data_ptr"):
+        return C.c_void_p(a.data_ptr())
+    return C.c_void_p(a.ctypes.data)
+
+
+# ------------------------------------------------------------------ functions.jl
+def read_quadrature(fname):
+    """src/functions.jl:33-63 -> (weights, θ_array, ϕ_array, n_points).  The point count comes from the table,
+    not from the digits after the first 'n' of the path (Q14)."""
+    tab = np.atleast_2d(np.loadtxt(fname, dtype=np.float64))
+    return tab[:, 0].copy(), tab[:, 1].copy(), tab[:, 2].copy(), tab.shape[0]
+
+
+QUADRATURE_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "quadratures")
+
+
+def quadrature_path(name):
+    """packaged copy of the reference's quadratures/<name>.dat (n1, n2, ul2n3, ul7n12, ul9n20)"""
+    return os.path.join(QUADRATURE_DIR, name + ".dat")
+
+
+def default_voro_exec():
+    here = os.path.dirname(os.path.abspath(__file__))
+    for p in (os.environ.get("VORO_EXEC"), "/root/reference/rt_preprocessing/output_sites",
+              os.path.join(here, "..", "oracle", "_ref", "output_sites")):
+        if p and os.path.exists(p) and os.access(p, os.X_OK):
+            return p
+    return None
+
+
+def write_arrays(x, y, z, fname):
+    """src/io.jl:8-40: one line per site, `id\\tx\\ty\\tz`, 1-based id."""
+    x, y, z = (np.asarray(a, dtype=np.float64) for a in (x, y, z))
+    ids = np.arange(1, len(x) + 1)
+    with open(fname, "w") as f:
+        for i, a, b, c in zip(ids, x, y, z):
+            f.write(f"{i}\t{a!r}\t{b!r}\t{c!r}\n")
+
+
+def voro(voro_executable, sites_file, neighbours_file, x_min, x_max, y_min, y_max, z_min, z_max):
+    """src/functions.jl:13-23: run the voro++ driver (rt_preprocessing/output_sites.cc) as a subprocess."""
+    subprocess.run([voro_executable, sites_file, neighbours_file, repr(float(x_min)), repr(float(x_max)),
+                    repr(float(y_min)), repr(float(y_max)), repr(float(z_min)), repr(float(z_max))],
+                   check=True, stdout=subprocess.DEVNULL)
+
+
+# ------------------------------------------------------------------ voronoi_utils.jl
+class _Grid:
+    """owner of a vrt_grid handle"""
+
+    def __init__(self, positions, nbr, bounds):
+        self.positions = _f(positions)
+        self.nbr = _f(nbr, np.int64)
+        self.n = self.positions.shape[1]
+        self.ld = self.nbr.shape[1]
+        b = np.ascontiguousarray(bounds, dtype=np.float64)
+        h = C.c_void_p()
+        check(lib().vrt_grid_create(self.n, _ptr(self.positions), _ptr(self.nbr), self.ld, _ptr(b), C.byref(h)))
+        self.h = h
+        self.solvers = {}
+
+    def __del__(self):
+        try:
+            for s in self.solvers.values():
+                s.close()
+            if self.h:
+                lib().vrt_grid_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def layers(self, down):
+        L = C.c_int64()
+        check(lib().vrt_grid_num_layers(self.h, down, C.byref(L)))
+        perm = np.zeros(self.n, dtype=np.int64)
+        off = np.zeros(L.value + 1, dtype=np.int64)
+        check(lib().vrt_grid_get_layers(self.h, down, _ptr(perm), _ptr(off)))
+        return perm, off
+
+    def delaunay_lines(self):
+        mx = C.c_int64()
+        check(lib().vrt_grid_size(self.h, None, C.byref(mx)))
+        out = np.zeros((3, mx.value, self.n), order="F")
+        check(lib().vrt_grid_get_delaunay_lines(self.h, _ptr(out)))
+        return out
+
+    def stencil(self, k, p=7.0):
+        k = np.ascontiguousarray(k, dtype=np.float64)
+        up = np.zeros((2, self.n), dtype=np.int64, order="F")
+        dots, w, r = (np.zeros((2, self.n), order="F") for _ in range(3))
+        check(lib().vrt_grid_get_stencil(self.h, _ptr(k), p, _ptr(up), _ptr(dots), _ptr(w), _ptr(r)))
+        return up, dots, w, r
+
+    def schedule(self, k, down, n_sweeps=3, prune=1):
+        k = np.ascontiguousarray(k, dtype=np.float64)
+        cls = np.zeros((2, self.n), dtype=np.int32, order="F")
+        sub = np.zeros(self.n, dtype=np.int32)
+        stab = np.zeros(self.n, dtype=np.int32)
+        ns, nv = C.c_int64(), C.c_int64()
+        check(lib().vrt_grid_get_schedule(self.h, _ptr(k), int(down), n_sweeps, prune, _ptr(cls), _ptr(sub), _ptr(stab),
+                                          C.byref(ns), C.byref(nv)))
+        return cls, sub, stab, ns.value, nv.value
+
+
+class _NeighbourMatrix(np.ndarray):
+    """NeighbourMatrix that remembers the device grid built from it by read_cell"""
+    _grid = None
+
+
+def read_neighbours(fname, n_sites):
+    """the parsing half of read_cell (src/voronoi_utils.jl:42-70) -> NeighbourMatrix (n, max_nb+1)"""
+    ld = C.c_int64()
+    check(lib().vrt_read_neighbours(fname.encode(), n_sites, None, 0, C.byref(ld)))
+    nbr = np.zeros((n_sites, ld.value), dtype=np.int64, order="F")
+    check(lib().vrt_read_neighbours(fname.encode(), n_sites, _ptr(nbr), ld.value, C.byref(ld)))
+    return nbr
+
+
+def read_cell(fname, n_sites, positions, x_min, x_max, y_min, y_max):
+    """src/voronoi_utils.jl:36-85 -> (positions, NeighbourMatrix, Delaunay_lines, layers_up, layers_down, perm_up, perm_down).
+
+    `fname` may also be an already parsed NeighbourMatrix.  Delaunay_lines is returned lazily as None-free
+    array only when small (< 2e6 entries); larger grids get an empty placeholder (the device keeps its own)."""
+    nbr = read_neighbours(fname, n_sites) if isinstance(fname, (str, bytes)) else _f(fname, np.int64)
+    positions = _f(positions)
+    g = _Grid(positions, nbr, [0.0, 0.0, x_min, x_max, y_min, y_max])
+    perm_up, layers_up = g.layers(0)
+    perm_down, layers_down = g.layers(1)
+    nm = nbr.view(_NeighbourMatrix)
+    nm._grid = g
+    lines = g.delaunay_lines() if 3 * n_sites * nbr.shape[1] < 2_000_000 else np.zeros((3, 0, n_sites), order="F")
+    return positions, nm, lines, layers_up, layers_down, perm_up, perm_down
+
+
+class VoronoiSites:
+    """src/voronoi_utils.jl:7-28 (same field names and order)."""
+
+    def __init__(self, positions, neighbours, Delaunay_lines, layers_up, layers_down, perm_up, perm_down,
+                 temperature, electron_density, hydrogen_populations, velocity_z, velocity_x, velocity_y,
+                 z_min, z_max, x_min, x_max, y_min, y_max, n):
+        self.positions = positions
+        self.neighbours = neighbours
+        self.Delaunay_lines = Delaunay_lines
+        self.layers_up, self.layers_down = layers_up, layers_down
+        self.perm_up, self.perm_down = perm_up, perm_down
+        self.temperature = np.asarray(temperature, dtype=np.float64)
+        self.electron_density = np.asarray(electron_density, dtype=np.float64)
+        self.hydrogen_populations = np.asarray(hydrogen_populations, dtype=np.float64)
+        self.velocity_z = np.asarray(velocity_z, dtype=np.float64)
+        self.velocity_x = np.asarray(velocity_x, dtype=np.float64)
+        self.velocity_y = np.asarray(velocity_y, dtype=np.float64)
+        self.z_min, self.z_max, self.x_min, self.x_max, self.y_min, self.y_max = z_min, z_max, x_min, x_max, y_min, y_max
+        self.n = n
+        g = getattr(neighbours, "_grid", None)
+        if g is None:
+            g = _Grid(positions, neighbours, [z_min, z_max, x_min, x_max, y_min, y_max])
+        self._grid = g
+
+
+def direction(θ, ϕ):
+    """k = [cos θ, cos ϕ sin θ, sin ϕ sin θ] on (z, x, y), degrees (src/lambda_iteration.jl:87)"""
+    t, p = θ * np.pi / 180, ϕ * np.pi / 180
+    return np.array([np.cos(t), np.cos(p) * np.sin(t), np.sin(p) * np.sin(t)])
+
+
+# ------------------------------------------------------------------ irregular_ray_tracing.jl
+def _formal(k, S, I_0, α, sites, n_sweeps, p, down):
+    S = _f(S)
+    α = _f(α)
+    nlam = 1 if S.ndim == 1 else S.shape[0]
+    I_0 = _f(I_0)
+    out = np.zeros_like(S, order="F")
+    k = np.ascontiguousarray(k, dtype=np.float64)
+    check(lib().vrt_formal_solve(sites._grid.h, _ptr(k), down, float(p), int(n_sweeps), nlam, _ptr(S), _ptr(α), _ptr(I_0), _ptr(out)))
+    return out
+
+
+def Delaunay_upII(k, S, I_0, α, sites, n_sweeps, p=7.0):
+    """src/irregular_ray_tracing.jl:15-82.  S, α: (n,) or (nλ, n); I_0: (n₁,) or (nλ, n₁) on perm_up[1:n₁]."""
+    return _formal(k, S, I_0, α, sites, n_sweeps, p, 0)
+
+
+def Delaunay_downII(k, S, I_0, α, sites, n_sweeps, p=7.0):
+    """src/irregular_ray_tracing.jl:96-163."""
+    return _formal(k, S, I_0, α, sites, n_sweeps, p, 1)
+
+
+# ------------------------------------------------------------------ Λ-iteration engine
+def _as_quadrature(quadrature):
+    if isinstance(quadrature, (str, bytes)):
+        w, t, p, _ = read_quadrature(quadrature)
+    else:
+        w, t, p = (np.ascontiguousarray(a, dtype=np.float64) for a in quadrature[:3])
+    q = _abi.vrt_quadrature(len(w), w.ctypes.data, t.ctypes.data, p.ctypes.data)
+    q._keep = (w, t, p)
+    return q
+
+
+class Solver:
+    """vrt_solver handle (state of Λ_voronoi).  kind: 'line' or 'continuum'."""
+
+    def __init__(self, sites, quadrature, line=None, α_cont=None, ελ=None, C_rates=None, LTE_pops=None, B_0=None,
+                 n_sweeps=3, p=7.0, lam_range=None, lam_chunk=0, prune=1):
+        self.sites = sites
+        self.line = line
+        q = _as_quadrature(quadrature)
+        cfg = _abi.vrt_config()
+        cfg.n_sweeps, cfg.p, cfg.prune, cfg.lam_chunk = n_sweeps, p, prune, lam_chunk
+        if lam_range is not None:
+            cfg.lam_begin, cfg.lam_end = lam_range
+        h = C.c_void_p()
+        n = sites.n
+        self._keep = []
+        if line is not None:
+            sd = _abi.vrt_site_data()
+
+            def put(name, a, shape=None):
+                if a is None:
+                    return
+                a = _f(a)
+                self._keep.append(a)
+                setattr(sd, name, a.ctypes.data)
+
+            put("temperature", sites.temperature)
+            put("electron_density", sites.electron_density)
+            put("hydrogen_density", sites.hydrogen_populations)
+            put("velocity_z", sites.velocity_z)
+            put("velocity_x", sites.velocity_x)
+            put("velocity_y", sites.velocity_y)
+            put("doppler_width", line.ΔD)
+            put("alpha_cont", α_cont if α_cont is not None else np.zeros(n))
+            put("destruction", ελ)
+            put("C", C_rates)
+            put("lte_pops", LTE_pops)
+            ls = line.as_struct()
+            lam = np.ascontiguousarray(line.λ, dtype=np.float64)
+            check(lib().vrt_solver_create_line(sites._grid.h, C.byref(ls), _ptr(lam), C.byref(sd), C.byref(q), C.byref(cfg), C.byref(h)))
+            self.kind = "line"
+        else:
+            a, e, b = _f(α_cont), _f(ελ), _f(B_0)
+            check(lib().vrt_solver_create_continuum(sites._grid.h, _ptr(a), _ptr(e), _ptr(b), C.byref(q), C.byref(cfg), C.byref(h)))
+            self.kind = "continuum"
+        self.h = h
+        nl = C.c_int64()
+        check(lib().vrt_solver_nlam_local(self.h, C.byref(nl)))
+        self.nlam = nl.value
+        self.n = n
+        self._cb = None
+        self._ar = None
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().vrt_solver_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    FIELDS = {"alpha_cont": 0, "destruction": 1, "C": 2, "lte_pops": 3}
+
+    def set_field(self, name, data):
+        a = data if hasattr(data, "data_ptr") else _f(data)
+        check(lib().vrt_solver_set_field(self.h, self.FIELDS[name], _ptr(a)))
+
+    def set_allreduce(self, fn):
+        """fn(dev_ptr:int, count:int, op:int) -> 0 on success; op 0 = sum, 1 = max"""
+        def tramp(ptr, count, op, user):
+            try:
+                return int(fn(ptr, count, op) or 0)
+            except Exception as ex:  # never let an exception cross the C boundary
+                print("allreduce hook failed:", ex)
+                return 1
+        self._ar = _abi.vrt_allreduce_fn(tramp)
+        check(lib().vrt_solver_set_allreduce(self.h, self._ar, None))
+
+    def mean_intensity(self, S, populations=None, J=None, damping=None):
+        """J_λ_voronoi on host arrays or device tensors (any of S, populations, J, damping may be a torch CUDA tensor)."""
+        if J is None:
+            J = np.zeros((self.nlam, self.n), order="F") if self.nlam > 1 or self.kind == "line" else np.zeros(self.n)
+        S_ = S if hasattr(S, "data_ptr") else _f(S)
+        P_ = populations if (populations is None or hasattr(populations, "data_ptr")) else _f(populations)
+        check(lib().vrt_mean_intensity(self.h, _ptr(S_), _ptr(P_), _ptr(J), _ptr(damping)))
+        return J
+
+    def calculate_R(self, J, damping=None, R=None):
+        if R is None:
+            R = np.zeros((3, 3, self.n), order="F")
+        J_ = J if hasattr(J, "data_ptr") else _f(J)
+        D_ = damping if (damping is None or hasattr(damping, "data_ptr")) else _f(damping)
+        check(lib().vrt_calculate_R(self.h, _ptr(J_), _ptr(D_), _ptr(R)))
+        return R
+
+    def iterate(self, ϵ, maxiter, callback=None):
+        res = _abi.vrt_result()
+        history = []
+
+        def tramp(info, user):
+            i = info.contents
+            rec = {f: getattr(i, f) for f, _ in _abi.vrt_iter_info._fields_ if f != "reserved0"}
+            history.append(rec)
+            try:
+                return int(callback(rec) or 0) if callback else 0
+            except Exception as ex:
+                print("iteration callback failed:", ex)
+                return 1
+        self._cb = _abi.vrt_iter_cb(tramp)
+        check(lib().vrt_lambda_iterate(self.h, float(ϵ), int(maxiter), self._cb, None, C.byref(res)))
+        return {"iterations": res.iterations, "converged": bool(res.converged), "diff": res.diff, "seconds": res.seconds,
+                "history": history}
+
+    def get_state(self):
+        shape = (self.nlam, self.n) if self.kind == "line" else (self.n,)
+        S = np.zeros(shape, order="F")
+        J = np.zeros(shape, order="F")
+        pops = np.zeros((self.n, 3), order="F") if self.kind == "line" else None
+        check(lib().vrt_get_state(self.h, _ptr(S), _ptr(J), _ptr(pops)))
+        return S, J, pops
+
+    def set_state(self, S=None, populations=None):
+        S_ = None if S is None else _f(S)
+        P_ = None if populations is None else _f(populations)
+        check(lib().vrt_set_state(self.h, _ptr(S_), _ptr(P_)))
+
+
+def _quad_key(quadrature):
+    if isinstance(quadrature, (str, bytes)):
+        return quadrature
+    return tuple(np.asarray(quadrature[0]).tolist()) + tuple(np.asarray(quadrature[1]).tolist())
+
+
+def _line_solver(sites, line, quadrature, **kw):
+    key = ("line", id(line), _quad_key(quadrature))
+    s = sites._grid.solvers.get(key)
+    if s is None:
+        s = Solver(sites, quadrature, line=line, **kw)
+        sites._grid.solvers[key] = s
+    return s
+
+
+def J_λ_voronoi(S_λ, α_cont, *args):
+    """Line form (src/lambda_iteration.jl:60-113): J_λ_voronoi(S_λ, α_cont, populations, sites, line, quadrature) -> (J_λ, damping_λ).
+    Continuum form (src/lambda_continuum.jl:27-56): J_λ_voronoi(S_λ, α_cont, sites, quadrature) -> J; the bottom boundary is
+    blackbody_λ(500 nm, T) evaluated from sites.temperature."""
+    if len(args) == 4:
+        populations, sites, line, quadrature = args
+        s = _line_solver(sites, line, quadrature, α_cont=α_cont)
+        s.set_field("alpha_cont", α_cont)
+        damping = np.zeros((s.nlam, s.n), order="F")
+        J = s.mean_intensity(S_λ, populations, damping=damping)
+        return J, damping
+    sites, quadrature = args
+    from .atom import B_λ
+    B0 = B_λ(500.0, sites.temperature)
+    s = Solver(sites, quadrature, α_cont=α_cont, ελ=np.ones(sites.n), B_0=B0)
+    try:
+        return s.mean_intensity(_f(S_λ).reshape(-1), J=np.zeros(sites.n))
+    finally:
+        s.close()
+
+
+def calculate_R(sites, line, J_λ, damping_λ, LTE_pops, quadrature=None):
+    """src/rates.jl:154-201 -> R (3, 3, n).  `quadrature` only selects which cached solver is reused."""
+    s = None
+    for key, cand in sites._grid.solvers.items():
+        if key[0] == "line" and key[1] == id(line) and (quadrature is None or key[2] == _quad_key(quadrature)):
+            s = cand
+            break
+    if s is None:
+        s = _line_solver(sites, line, quadrature if quadrature is not None else quadrature_path("n1"))
+    s.set_field("lte_pops", LTE_pops)
+    return s.calculate_R(J_λ, damping_λ)
+
+
+def get_revised_populations(R, C_rates, atom_density):
+    """src/populations.jl:191-221 -> populations (n, 3)."""
+    R, C_rates, NH = _f(R), _f(C_rates), _f(atom_density)
+    n = NH.shape[0]
+    pops = np.zeros((n, 3), order="F")
+    check(lib().vrt_get_revised_populations(n, _ptr(R), _ptr(C_rates), _ptr(NH), _ptr(pops)))
+    return pops
+
+
+def Λ_voronoi(ϵ, maxiter, sites, *args, **kw):
+    """Line form (src/lambda_iteration.jl:207-297): Λ_voronoi(ϵ, maxiter, sites, line, quadrature, DATA=None;
+    α_cont, ελ, C, LTE_pops) -> (J, S, α_cont, populations).  The four keyword arrays are what the reference
+    computes with Transparency.jl before its loop (:216-247).
+    Continuum form (src/lambda_continuum.jl:109-160): Λ_voronoi(ϵ, maxiter, sites, quadrature; α_cont, ε_λ, B_0) -> (J, S, α_cont)."""
+    callback = kw.pop("callback", None)
+    if len(args) >= 2 and not isinstance(args[0], (str, bytes, tuple, list)):
+        line, quadrature = args[0], args[1]
+        s = Solver(sites, quadrature, line=line, α_cont=kw["α_cont"], ελ=kw["ελ"], C_rates=kw["C"], LTE_pops=kw["LTE_pops"],
+                   **{k: v for k, v in kw.items() if k in ("n_sweeps", "p", "lam_range", "lam_chunk", "prune")})
+        try:
+            res = s.iterate(ϵ, maxiter, callback)
+            S, J, pops = s.get_state()
+        finally:
+            s.close()
+        Λ_voronoi.last = res
+        return J, S, _f(kw["α_cont"]), pops
+    quadrature = args[0]
+    s = Solver(sites, quadrature, α_cont=kw["α_cont"], ελ=kw["ε_λ"], B_0=kw["B_0"])
+    try:
+        res = s.iterate(ϵ, maxiter, callback)
+        S, J, _ = s.get_state()
+    finally:
+        s.close()
+    Λ_voronoi.last = res
+    return J, S, _f(kw["α_cont"])
+
+
+# ASCII aliases
+J_lambda_voronoi = J_λ_voronoi
+Lambda_voronoi = Λ_voronoi

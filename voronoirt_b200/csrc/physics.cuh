@@ -1,0 +1,100 @@
+// physics.cuh — device-side physics shared by the opacity (K4), source (K6) and rates (K7) kernels.
+// Constants are CODATA 2018 as used by the reference (src/atmosphere.jl:1-8 via PhysicalConstants).
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+
+namespace vrt {
+
+constexpr double H_PLANCK = 6.62607015e-34;
+constexpr double K_B = 1.380649e-23;
+constexpr double C_0 = 299792458.0;
+constexpr double E_CHARGE = 1.602176634e-19;
+constexpr double M_ELECTRON = 9.1093837015e-31;
+constexpr double EPS_0 = 8.8541878128e-12;
+constexpr double R_INF = 10973731.568160;
+constexpr double PI = 3.14159265358979323846;
+constexpr double INV_SQRT_PI = 0.5641895835477563;
+
+struct cplx {
+    double re, im;
+};
+__host__ __device__ __forceinline__ cplx c_mul(cplx a, cplx b) { return {a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re}; }
+__host__ __device__ __forceinline__ cplx c_add_r(double x, cplx a) { return {x + a.re, a.im}; }
+__host__ __device__ __forceinline__ cplx c_rsub(double x, cplx a) { return {x - a.re, -a.im}; }
+__host__ __device__ __forceinline__ cplx c_scale(double x, cplx a) { return {x * a.re, x * a.im}; }
+__host__ __device__ __forceinline__ cplx c_div(cplx a, cplx b) {
+    double den = b.re * b.re + b.im * b.im;
+    return {(a.re * b.re + a.im * b.im) / den, (a.im * b.re - a.re * b.im) / den};
+}
+
+// Re w(v + i a), Humlíček (1982) w4 — what Transparency.jl's voigt_profile evaluates
+// (call sites: reference src/line.jl:133, src/rates.jl:408).
+__device__ __forceinline__ double humlicek_re(double a, double v) {
+    cplx z = {v, a};
+    double s = fabs(v) + a;
+    if (s > 15.0) {
+        cplx zz = c_mul(z, z);
+        cplx den = {zz.re - 0.5, zz.im};
+        cplx num = {-INV_SQRT_PI * z.im, INV_SQRT_PI * z.re};
+        return c_div(num, den).re;
+    } else if (s > 5.5) {
+        cplx zz = c_mul(z, z);
+        cplx t1 = {zz.re * INV_SQRT_PI - 1.4104739589, zz.im * INV_SQRT_PI};
+        cplx zt = c_mul(z, t1);
+        cplx num = {-zt.im, zt.re};
+        cplx zz3 = {zz.re - 3.0, zz.im};
+        cplx den = c_add_r(0.75, c_mul(zz, zz3));
+        return c_div(num, den).re;
+    } else {
+        double x = v, y = a;
+        cplx t = {y, -x};
+        if (y >= 0.195 * fabs(x) - 0.176) {
+            cplx num = c_add_r(3.778987, c_scale(0.5642236, t));
+            num = c_add_r(11.96482, c_mul(t, num));
+            num = c_add_r(20.20933, c_mul(t, num));
+            num = c_add_r(16.4955, c_mul(t, num));
+            cplx den = c_add_r(6.699398, t);
+            den = c_add_r(21.69274, c_mul(t, den));
+            den = c_add_r(39.27121, c_mul(t, den));
+            den = c_add_r(38.82363, c_mul(t, den));
+            den = c_add_r(16.4955, c_mul(t, den));
+            return c_div(num, den).re;
+        } else {
+            cplx u = c_mul(t, t);
+            cplx num = c_rsub(1.320522, c_scale(0.56419, u));
+            num = c_rsub(35.7668, c_mul(u, num));
+            num = c_rsub(219.031, c_mul(u, num));
+            num = c_rsub(1540.787, c_mul(u, num));
+            num = c_rsub(3321.99, c_mul(u, num));
+            num = c_rsub(36183.31, c_mul(u, num));
+            num = c_mul(t, num);
+            cplx den = c_rsub(1.84144, u);
+            den = c_rsub(61.5704, c_mul(u, den));
+            den = c_rsub(364.219, c_mul(u, den));
+            den = c_rsub(2186.18, c_mul(u, den));
+            den = c_rsub(9022.23, c_mul(u, den));
+            den = c_rsub(24322.8, c_mul(u, den));
+            den = c_rsub(32066.6, c_mul(u, den));
+            cplx q = c_div(num, den);
+            return exp(u.re) * cos(u.im) - q.re;
+        }
+    }
+}
+
+// voigt_profile(a, v, ΔD) with ΔD in metres -> m^-1
+__device__ __forceinline__ double voigt_profile(double a, double v, double dD_m) { return humlicek_re(a, v) / (sqrt(PI) * dD_m); }
+
+// B_λ (reference src/radiation.jl:17-19) in kW m^-2 nm^-1, λ in nm
+__device__ __forceinline__ double B_lambda(double lambda_nm, double T) {
+    double lam = lambda_nm * 1e-9;
+    double lam5 = lam * lam * lam * lam * lam;
+    return 2 * H_PLANCK * C_0 * C_0 / lam5 * 1 / (exp(H_PLANCK * C_0 / (lam * K_B * T)) - 1) * 1e-12;
+}
+
+// damping (reference src/broadening.jl:87-89), λ and ΔD in nm
+__device__ __forceinline__ double damping_param(double gamma, double lambda_nm, double dD_nm) {
+    return gamma * (lambda_nm * lambda_nm) / (4 * PI * C_0 * dD_nm) * 1e-9;
+}
+
+}  // namespace vrt

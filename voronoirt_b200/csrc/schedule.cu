@@ -1,0 +1,363 @@
+// schedule.cu — K3: turns the sequential in-layer Gauss–Seidel sweep of Delaunay_upII/downII
+// (reference src/irregular_ray_tracing.jl:37-80, :118-161) into a parallel program that produces the same
+// numbers:
+//
+//   1. classify each upwind reference of each processed cell: FINAL (lower layer), THIS (same layer,
+//      earlier in the loop order: reads this sweep's value), LAG (same layer, later: reads the previous
+//      sweep's value, 0 in sweep 1), ZERO (higher layer or the never-processed last-rank site, Q1/Q5);
+//   2. chg[s][c] = "the value of c computed in sweep s can differ from sweep s-1" (structural, exact):
+//      chg[1] = processed; chg[s] = OR_LAG chg[s-1][u]  OR_THIS chg[s][u].  stab(c) = #s with chg[s][c].
+//      With prune=0 every processed cell is visited n_sweeps times like the reference does;
+//   3. sub-levels per sweep over the active cells: sub_s(c) = 1 + max sub_s(u) over active THIS refs;
+//   4. a VISIT per (c, s <= stab(c)), sorted by step = (layer, sweep, sub-level); all operands are
+//      resolved to (buffer,row): sweep-s values of cells with stab > s live in scratch buffer s, the final
+//      value in the main intensity array, so there is no write-after-read hazard between sweeps.
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+#include <string.h>
+#include "vrt_internal.h"
+
+namespace vrt {
+
+static inline int nblocks(int64_t n, int bs) { return (int)((n + bs - 1) / bs); }
+
+struct DirCtx {
+    const int32_t* layer;  // 1-based layer of each internal cell
+    const int32_t* ord;    // rank in the direction's perm (nullptr: up, ord = c)
+    int down;
+    int32_t X;             // never-processed cell (last rank)
+    int64_t n;
+};
+
+__device__ __forceinline__ bool processed(const DirCtx& d, int64_t c) { return d.layer[c] >= 2 && c != d.X; }
+// true when u is visited before c inside one sweep of their common layer (up ascending rank, down descending)
+__device__ __forceinline__ bool before(const DirCtx& d, int32_t u, int32_t c) {
+    if (!d.down) return u < c;
+    return d.ord[u] > d.ord[c];
+}
+
+__global__ void k_classify(DirCtx d, const int32_t* __restrict__ up, int32_t* __restrict__ cls, int* __restrict__ bad) {
+    int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (c >= d.n) return;
+    if (!processed(d, c)) {
+        cls[2 * c] = cls[2 * c + 1] = -1;
+        return;
+    }
+    int32_t lc = d.layer[c];
+    for (int m = 0; m < 2; m++) {
+        int32_t u = up[2 * c + m];
+        int32_t k;
+        if (u < 0) k = CLS_ZERO;  // no positive neighbour at all (the reference would index garbage)
+        else if (u == (int32_t)c) { k = CLS_ZERO; atomicExch(bad, 1); }
+        else if (u == d.X) k = CLS_ZERO;
+        else if (d.layer[u] < lc) k = CLS_FINAL;
+        else if (d.layer[u] > lc) k = CLS_ZERO;
+        else k = before(d, u, (int32_t)c) ? CLS_THIS : CLS_LAG;
+        cls[2 * c + m] = k;
+    }
+}
+
+__global__ void k_chg_init(DirCtx d, uint8_t* __restrict__ chg) {
+    int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (c < d.n) chg[c] = processed(d, c) ? 1 : 0;
+}
+
+// base of sweep s: OR over LAG references of chg[s-1]
+__global__ void k_chg_base(int64_t n, const int32_t* __restrict__ up, const int32_t* __restrict__ cls,
+                           const uint8_t* __restrict__ prev, uint8_t* __restrict__ cur) {
+    int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (c >= n) return;
+    uint8_t v = 0;
+    for (int m = 0; m < 2; m++)
+        if (cls[2 * c + m] == CLS_LAG && prev[up[2 * c + m]]) v = 1;
+    cur[c] = v;
+}
+
+// propagate along THIS references until a fixed point (monotone, so in-place Jacobi is safe)
+__global__ void k_chg_relax(int64_t n, const int32_t* __restrict__ up, const int32_t* __restrict__ cls,
+                            uint8_t* cur, int* __restrict__ changed) {
+    int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (c >= n || cur[c]) return;
+    for (int m = 0; m < 2; m++)
+        if (cls[2 * c + m] == CLS_THIS && cur[up[2 * c + m]]) {
+            cur[c] = 1;
+            *changed = 1;
+            return;
+        }
+}
+
+__global__ void k_sub_init(int64_t n, const uint8_t* __restrict__ chg, int32_t* __restrict__ sub) {
+    int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (c < n) sub[c] = chg[c] ? 1 : 0;
+}
+
+__global__ void k_sub_relax(int64_t n, const int32_t* __restrict__ up, const int32_t* __restrict__ cls,
+                            const uint8_t* __restrict__ chg, int32_t* sub, int* __restrict__ changed) {
+    int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (c >= n || !chg[c]) return;
+    int32_t s = sub[c], want = 1;
+    for (int m = 0; m < 2; m++)
+        if (cls[2 * c + m] == CLS_THIS) {
+            int32_t u = up[2 * c + m];
+            if (chg[u]) {
+                int32_t su = ((volatile int32_t*)sub)[u] + 1;
+                want = su > want ? su : want;
+            }
+        }
+    if (want > s) {
+        sub[c] = want;
+        *changed = 1;
+    }
+}
+
+__global__ void k_nsub(int64_t n, const int32_t* __restrict__ layer, const int32_t* __restrict__ sub, int n_sweeps, int s,
+                       int32_t* __restrict__ nsub) {
+    int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (c >= n) return;
+    int32_t v = sub[c];
+    if (v > 0) atomicMax(&nsub[(layer[c] - 2) * n_sweeps + (s - 1)], v);
+}
+
+__global__ void k_stab_acc(int64_t n, const uint8_t* __restrict__ chg, int32_t* __restrict__ stab, int first) {
+    int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (c < n) stab[c] = (first ? 0 : stab[c]) + (chg[c] ? 1 : 0);
+}
+
+__global__ void k_flag_gt(int64_t n, const int32_t* __restrict__ stab, int s, int32_t* __restrict__ flag) {
+    int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (c < n) flag[c] = stab[c] > s ? 1 : 0;
+}
+
+// emit (key = local step, val = sweep<<29 | cell) for every visit, in cell order
+__global__ void k_emit(int64_t n, const int32_t* __restrict__ layer, const int32_t* __restrict__ stab,
+                       const int64_t* __restrict__ voff, const int32_t* __restrict__ sub_all /* [s][n] */,
+                       const int32_t* __restrict__ stepbase /* [(layer-2)*S + s-1] */, int n_sweeps,
+                       uint32_t* __restrict__ key, uint32_t* __restrict__ val) {
+    int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (c >= n) return;
+    int32_t st = stab[c];
+    int64_t o = voff[c];
+    for (int s = 1; s <= st; s++) {
+        int32_t t = stepbase[(layer[c] - 2) * n_sweeps + (s - 1)] + sub_all[(int64_t)(s - 1) * n + c] - 1;
+        key[o + s - 1] = (uint32_t)t;
+        val[o + s - 1] = ((uint32_t)s << SEL_SHIFT) | (uint32_t)c;
+    }
+}
+
+__global__ void k_step_bounds(int64_t V, const uint32_t* __restrict__ key, int64_t* __restrict__ off) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= V) return;
+    if (i == 0 || key[i] != key[i - 1]) off[key[i]] = i;
+}
+
+__device__ __forceinline__ uint32_t resolve(int32_t u, int t, const int32_t* __restrict__ stab,
+                                            const int32_t* __restrict__ slots /* [s][n] */, int64_t n) {
+    if (t <= 0) return SEL_ZERO << SEL_SHIFT;
+    if (t >= stab[u]) return (SEL_MAIN << SEL_SHIFT) | (uint32_t)u;
+    return ((SEL_SCR0 + (uint32_t)(t - 1)) << SEL_SHIFT) | (uint32_t)slots[(int64_t)(t - 1) * n + u];
+}
+
+__global__ void k_build_visits(int64_t V, int64_t n, const uint32_t* __restrict__ val, const int32_t* __restrict__ up,
+                               const int32_t* __restrict__ cls, const int32_t* __restrict__ stab,
+                               const int32_t* __restrict__ slots, const double* __restrict__ w, const double* __restrict__ r,
+                               Visit* __restrict__ out) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= V) return;
+    uint32_t v = val[i];
+    int s = (int)(v >> SEL_SHIFT);
+    int32_t c = (int32_t)(v & ROW_MASK);
+    Visit o;
+    o.cell = (uint32_t)c;
+    o.dst = (s == stab[c]) ? ((SEL_MAIN << SEL_SHIFT) | (uint32_t)c)
+                           : (((SEL_SCR0 + (uint32_t)(s - 1)) << SEL_SHIFT) | (uint32_t)slots[(int64_t)(s - 1) * n + c]);
+    uint32_t src[2], uu[2];
+    for (int m = 0; m < 2; m++) {
+        int32_t u = up[2 * c + m];
+        int32_t k = cls[2 * c + m];
+        uu[m] = u >= 0 ? (uint32_t)u : (uint32_t)c;
+        if (k == CLS_FINAL) src[m] = (SEL_MAIN << SEL_SHIFT) | (uint32_t)u;
+        else if (k == CLS_THIS) src[m] = resolve(u, s, stab, slots, n);
+        else if (k == CLS_LAG) src[m] = resolve(u, s - 1, stab, slots, n);
+        else src[m] = SEL_ZERO << SEL_SHIFT;
+    }
+    o.u1 = uu[0]; o.u2 = uu[1];
+    o.src1 = src[0]; o.src2 = src[1];
+    o.pad0 = o.pad1 = 0;
+    o.w1 = w[2 * c]; o.w2 = w[2 * c + 1];
+    o.hr1 = 0.5 * r[2 * c]; o.hr2 = 0.5 * r[2 * c + 1];
+    out[i] = o;
+}
+
+static int relax_loop(void (*launch)(void*), void* ctx, int* d_flag, int max_iter) {
+    for (int it = 0; it < max_iter; it++) {
+        VRT_CUDA(cudaMemsetAsync(d_flag, 0, sizeof(int)));
+        launch(ctx);
+        VRT_CUDA(cudaGetLastError());
+        int h = 0;
+        VRT_CUDA(cudaMemcpy(&h, d_flag, sizeof(int), cudaMemcpyDeviceToHost));
+        if (!h) return VRT_OK;
+    }
+    set_error("schedule relaxation did not converge");
+    return VRT_E_STATE;
+}
+
+int schedule_build(vrt_grid* g, const double k[3], int down, int n_sweeps, double p, int prune, DirSchedule** out) {
+    *out = nullptr;
+    if (n_sweeps < 1 || n_sweeps > MAX_SWEEPS - 1) {
+        set_error("n_sweeps=%d unsupported (1..%d)", n_sweeps, MAX_SWEEPS - 1);
+        return VRT_E_INVALID;
+    }
+    const int64_t n = g->n;
+    const int bs = 256;
+    const int nb = nblocks(n, bs);
+    const int64_t L = down ? g->L_down : g->L_up;
+    DirSchedule* sch = new DirSchedule();
+    struct Guard { DirSchedule* s; ~Guard() { delete s; } } guard{sch};
+    memcpy(sch->k, k, sizeof(double) * 3);
+    sch->down = down; sch->n_sweeps = n_sweeps; sch->p = p; sch->prune = prune;
+
+    Stencil st;
+    VRT_TRY(grid_stencil(g, k, p, &st));
+
+    DirCtx d;
+    d.layer = down ? g->layer_dn.p : g->layer_up.p;
+    d.ord = down ? g->rank_dn.p : nullptr;
+    d.down = down;
+    d.n = n;
+    if (down) {
+        VRT_CUDA(cudaMemcpy(&d.X, g->perm_dn_int.p + (n - 1), sizeof(int32_t), cudaMemcpyDeviceToHost));
+    } else
+        d.X = (int32_t)(n - 1);
+
+    DevBuf<int> flag;
+    VRT_TRY(flag.alloc(1));
+    VRT_CUDA(cudaMemset(flag.p, 0, sizeof(int)));
+    VRT_TRY(sch->cls.alloc(2 * n)); VRT_TRY(sch->sublevel.alloc(n)); VRT_TRY(sch->stab.alloc(n));
+    k_classify<<<nb, bs>>>(d, st.up.p, sch->cls.p, flag.p);
+    VRT_CUDA(cudaGetLastError());
+    {
+        int h = 0;
+        VRT_CUDA(cudaMemcpy(&h, flag.p, sizeof(int), cudaMemcpyDeviceToHost));
+        if (h) {
+            set_error("a site is its own upwind neighbour (periodic self-image); not supported");
+            return VRT_E_GRID;
+        }
+    }
+
+    const int S = n_sweeps;
+    const int64_t nls = (L >= 2 ? (L - 1) : 0) * S;  // (layer 2..L) x sweeps
+    DevBuf<uint8_t> chg;      // [S][n]
+    DevBuf<int32_t> sub_all;  // [S][n]
+    DevBuf<int32_t> nsub;
+    VRT_TRY(chg.alloc((size_t)S * n)); VRT_TRY(sub_all.alloc((size_t)S * n)); VRT_TRY(nsub.alloc(nls > 0 ? nls : 1));
+    VRT_CUDA(cudaMemset(nsub.p, 0, sizeof(int32_t) * (nls > 0 ? nls : 1)));
+
+    for (int s = 1; s <= S; s++) {
+        uint8_t* cur = chg.p + (size_t)(s - 1) * n;
+        if (s == 1 || !prune) {
+            k_chg_init<<<nb, bs>>>(d, cur);
+        } else {
+            const uint8_t* prev = chg.p + (size_t)(s - 2) * n;
+            k_chg_base<<<nb, bs>>>(n, st.up.p, sch->cls.p, prev, cur);
+            struct C { int nb, bs; int64_t n; const int32_t *up, *cls; uint8_t* cur; int* flag; } cx{nb, bs, n, st.up.p, sch->cls.p, cur, flag.p};
+            VRT_TRY(relax_loop([](void* v) { C* c = (C*)v; k_chg_relax<<<c->nb, c->bs>>>(c->n, c->up, c->cls, c->cur, c->flag); }, &cx, flag.p, 100000));
+        }
+        k_stab_acc<<<nb, bs>>>(n, cur, sch->stab.p, s == 1);
+        int32_t* sub = sub_all.p + (size_t)(s - 1) * n;
+        k_sub_init<<<nb, bs>>>(n, cur, sub);
+        struct C2 { int nb, bs; int64_t n; const int32_t *up, *cls; const uint8_t* chg; int32_t* sub; int* flag; } c2{nb, bs, n, st.up.p, sch->cls.p, cur, sub, flag.p};
+        VRT_TRY(relax_loop([](void* v) { C2* c = (C2*)v; k_sub_relax<<<c->nb, c->bs>>>(c->n, c->up, c->cls, c->chg, c->sub, c->flag); }, &c2, flag.p, 100000));
+        if (nls > 0) k_nsub<<<nb, bs>>>(n, d.layer, sub, S, s, nsub.p);
+        VRT_CUDA(cudaGetLastError());
+    }
+    VRT_CUDA(cudaMemcpy(sch->sublevel.p, sub_all.p, sizeof(int32_t) * n, cudaMemcpyDeviceToDevice));
+
+    // local step numbering: (layer asc, sweep asc, sub-level asc)
+    sch->nsub.assign((size_t)nls, 0);
+    if (nls > 0) VRT_CUDA(cudaMemcpy(sch->nsub.data(), nsub.p, sizeof(int32_t) * nls, cudaMemcpyDeviceToHost));
+    std::vector<int32_t> stepbase((size_t)(nls > 0 ? nls : 1), 0);
+    int64_t T = 0;
+    for (int64_t i = 0; i < nls; i++) {
+        stepbase[i] = (int32_t)T;
+        T += sch->nsub[i];
+    }
+    DevBuf<int32_t> d_stepbase;
+    VRT_TRY(d_stepbase.alloc(stepbase.size()));
+    VRT_CUDA(cudaMemcpy(d_stepbase.p, stepbase.data(), sizeof(int32_t) * stepbase.size(), cudaMemcpyHostToDevice));
+
+    // visit offsets = exclusive scan of stab; scratch slots = exclusive scan of [stab > s]
+    DevBuf<int64_t> voff;
+    DevBuf<int32_t> slots, flags;
+    DevBuf<char> tmp;
+    VRT_TRY(voff.alloc(n + 1)); VRT_TRY(slots.alloc((size_t)(S > 1 ? S - 1 : 1) * n)); VRT_TRY(flags.alloc(n));
+    size_t tb1 = 0, tb2 = 0;
+    VRT_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb1, sch->stab.p, voff.p, (int)n));
+    VRT_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb2, flags.p, slots.p, (int)n));
+    VRT_TRY(tmp.alloc(tb1 > tb2 ? tb1 : tb2));
+    size_t tb = tmp.n;
+    VRT_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, sch->stab.p, voff.p, (int)n));
+    int64_t V = 0;
+    {
+        int64_t lastoff = 0;
+        int32_t laststab = 0;
+        VRT_CUDA(cudaMemcpy(&lastoff, voff.p + (n - 1), sizeof(int64_t), cudaMemcpyDeviceToHost));
+        VRT_CUDA(cudaMemcpy(&laststab, sch->stab.p + (n - 1), sizeof(int32_t), cudaMemcpyDeviceToHost));
+        V = lastoff + laststab;
+    }
+    for (int s = 1; s < S; s++) {
+        k_flag_gt<<<nb, bs>>>(n, sch->stab.p, s, flags.p);
+        tb = tmp.n;
+        VRT_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, flags.p, slots.p + (size_t)(s - 1) * n, (int)n));
+        int32_t lo = 0, lf = 0;
+        VRT_CUDA(cudaMemcpy(&lo, slots.p + (size_t)(s - 1) * n + (n - 1), sizeof(int32_t), cudaMemcpyDeviceToHost));
+        VRT_CUDA(cudaMemcpy(&lf, flags.p + (n - 1), sizeof(int32_t), cudaMemcpyDeviceToHost));
+        sch->scr_rows[s - 1] = (int64_t)lo + lf;
+    }
+    sch->n_visits = V;
+    sch->step_off.assign((size_t)T + 1, 0);
+    if (V > 0) {
+        if (V >= (int64_t)INT32_MAX) {
+            set_error("too many visits (%lld) for one direction", (long long)V);
+            return VRT_E_INVALID;
+        }
+        DevBuf<uint32_t> key, val, key2, val2;
+        VRT_TRY(key.alloc(V)); VRT_TRY(val.alloc(V)); VRT_TRY(key2.alloc(V)); VRT_TRY(val2.alloc(V));
+        k_emit<<<nb, bs>>>(n, d.layer, sch->stab.p, voff.p, sub_all.p, d_stepbase.p, S, key.p, val.p);
+        VRT_CUDA(cudaGetLastError());
+        int bits = 1;
+        while ((1ll << bits) < T + 1 && bits < 32) bits++;
+        size_t sb = 0;
+        VRT_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, sb, key.p, key2.p, val.p, val2.p, (int)V, 0, bits));
+        DevBuf<char> stmp;
+        VRT_TRY(stmp.alloc(sb));
+        VRT_CUDA(cub::DeviceRadixSort::SortPairs(stmp.p, sb, key.p, key2.p, val.p, val2.p, (int)V, 0, bits));
+        DevBuf<int64_t> off;
+        VRT_TRY(off.alloc(T + 1));
+        k_step_bounds<<<nblocks(V, bs), bs>>>(V, key2.p, off.p);
+        VRT_CUDA(cudaMemcpy(sch->step_off.data(), off.p, sizeof(int64_t) * T, cudaMemcpyDeviceToHost));
+        sch->step_off[T] = V;
+        VRT_TRY(sch->visits.alloc(V));
+        k_build_visits<<<nblocks(V, bs), bs>>>(V, n, val2.p, st.up.p, sch->cls.p, sch->stab.p, slots.p, st.w.p, st.r.p, sch->visits.p);
+        VRT_CUDA(cudaGetLastError());
+    }
+    VRT_CUDA(cudaDeviceSynchronize());
+    guard.s = nullptr;
+    *out = sch;
+    return VRT_OK;
+}
+
+DirSchedule* schedule_get(vrt_grid* g, const double k[3], int down, int n_sweeps, double p, int prune, int* rc) {
+    for (auto* s : g->cache)
+        if (s->k[0] == k[0] && s->k[1] == k[1] && s->k[2] == k[2] && s->down == down && s->n_sweeps == n_sweeps &&
+            s->p == p && s->prune == prune) {
+            *rc = VRT_OK;
+            return s;
+        }
+    DirSchedule* s = nullptr;
+    *rc = schedule_build(g, k, down, n_sweeps, p, prune, &s);
+    if (*rc != VRT_OK) return nullptr;
+    g->cache.push_back(s);
+    return s;
+}
+
+}  // namespace vrt

@@ -1,0 +1,169 @@
+// vrt_internal.h — internal structures of libvrt.so (not part of the ABI).
+//
+// Data layout in HBM:
+//   * internal cell id c = 0-based rank of the site in perm_up (sites of one BFS layer are contiguous);
+//     every per-site array is stored in that order, every nlam x n array as [c][l] with l fastest.
+//   * per direction: a list of VISITS sorted by dependent step; a visit is one (cell, sweep) evaluation
+//     of irregular_ray_tracing.jl:41-77 with all its operands resolved to (buffer, row) pairs.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+#include "../../include/vrt.h"
+
+namespace vrt {
+
+// ---------------------------------------------------------------- errors
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
+
+#define VRT_CUDA(call)                                                         \
+    do {                                                                       \
+        cudaError_t _e = (call);                                               \
+        if (_e != cudaSuccess) return ::vrt::cuda_fail(_e, #call, __FILE__, __LINE__); \
+    } while (0)
+#define VRT_TRY(call)            \
+    do {                         \
+        int _r = (call);         \
+        if (_r != VRT_OK) return _r; \
+    } while (0)
+
+// ---------------------------------------------------------------- device buffers
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    DevBuf() {}
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    ~DevBuf() { release(); }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+    int alloc(size_t count) {
+        release();
+        if (count == 0) count = 1;
+        cudaError_t e = cudaMalloc((void**)&p, count * sizeof(T));
+        if (e != cudaSuccess) {
+            p = nullptr;
+            set_error("cudaMalloc of %zu bytes failed: %s", count * sizeof(T), cudaGetErrorString(e));
+            cudaGetLastError();
+            return VRT_E_NOMEM;
+        }
+        n = count;
+        return VRT_OK;
+    }
+    int ensure(size_t count) { return (count <= n && p) ? VRT_OK : alloc(count); }
+};
+
+bool is_device_ptr(const void* p);
+// copy `bytes` from a host-or-device pointer to device memory (and back)
+int copy_in(void* dst_dev, const void* src, size_t bytes, cudaStream_t st = 0);
+int copy_out(void* dst, const void* src_dev, size_t bytes, cudaStream_t st = 0);
+
+// ---------------------------------------------------------------- sweep program
+// operand selector: top 3 bits of a 32-bit word = buffer, low 29 bits = row
+enum : uint32_t { SEL_ZERO = 0u, SEL_MAIN = 1u, SEL_SCR0 = 2u /* SEL_SCR0 + (sweep-1) */ };
+constexpr uint32_t SEL_SHIFT = 29;
+constexpr uint32_t ROW_MASK = (1u << SEL_SHIFT) - 1u;
+constexpr int MAX_SWEEPS = 6;            // scratch selectors 2..6 -> sweeps 1..5 non-final
+constexpr int MAX_DIRS = 32;             // directions merged into one sweep launch
+
+// reference classes (SURVEY App. G rule 2)
+enum : int32_t { CLS_FINAL = 0, CLS_THIS = 1, CLS_LAG = 2, CLS_ZERO = 3 };
+
+struct __align__(16) Visit {
+    uint32_t cell;   // row of S / alpha of the cell itself
+    uint32_t dst;    // selector|row the result is written to
+    uint32_t u1, u2; // rows of S / alpha of the two upwind cells
+    uint32_t src1, src2;  // selector|row the upwind intensities are read from
+    uint32_t pad0, pad1;
+    double w1, w2;   // dot_weights (irregular_ray_tracing.jl:51)
+    double hr1, hr2; // r/2 (euclidean, :66; the /2 of trapezoidal, functions.jl:393)
+};
+static_assert(sizeof(Visit) == 64, "Visit must be 64 bytes");
+
+// per-direction stencil in internal order
+struct Stencil {
+    DevBuf<int32_t> up;     // 2*n internal ids (or -1)
+    DevBuf<double> dots;    // 2*n
+    DevBuf<double> w;       // 2*n
+    DevBuf<double> r;       // 2*n
+};
+
+struct DirSchedule {
+    double k[3];
+    int down = 0;
+    int n_sweeps = 3;
+    int prune = 1;
+    double p = 7.0;
+    DevBuf<Visit> visits;           // V records sorted by local step
+    int64_t n_visits = 0;
+    std::vector<int64_t> step_off;  // local steps: T_local+1 offsets into visits
+    // (layer, sweep) -> number of sub-levels; index (layer-2)*n_sweeps + (sweep-1)
+    std::vector<int32_t> nsub;
+    int64_t scr_rows[MAX_SWEEPS] = {0};  // rows needed in scratch buffer s (sweep s+1 non-final writers)
+    // introspection (internal order)
+    DevBuf<int32_t> cls;       // 2*n
+    DevBuf<int32_t> sublevel;  // n (sweep 1)
+    DevBuf<int32_t> stab;      // n
+};
+
+}  // namespace vrt
+
+// ---------------------------------------------------------------- opaque handles
+struct vrt_grid {
+    int64_t n = 0, ld = 0, max_nb = 0;
+    double bounds[6];
+    int device = 0;
+    // host copies (ABI order, 1-based)
+    std::vector<int64_t> perm_up, perm_down, off_up, off_down;
+    int64_t L_up = 0, L_down = 0;
+    // device, internal order
+    vrt::DevBuf<double> pos;         // 3*n, [c][3] (z,x,y)
+    vrt::DevBuf<int32_t> nbr;        // max_nb*n, [j][c]: internal id, or negative wall code, or INT_MIN (empty)
+    vrt::DevBuf<int32_t> nnb;        // n
+    vrt::DevBuf<int32_t> site_of;    // n: internal id -> 0-based host site
+    vrt::DevBuf<int32_t> rank_of;    // n: 0-based host site -> internal id
+    vrt::DevBuf<int32_t> layer_up;   // n: 1-based up layer of internal cell
+    vrt::DevBuf<int32_t> layer_dn;   // n
+    vrt::DevBuf<int32_t> rank_dn;    // n: 0-based rank in perm_down of internal cell
+    vrt::DevBuf<int32_t> perm_dn_int;// n: rank in perm_down -> internal id
+    // cached schedules (keyed by direction, down, n_sweeps, p, prune)
+    std::vector<vrt::DirSchedule*> cache;
+    ~vrt_grid();
+};
+
+namespace vrt {
+
+// grid.cu
+int grid_build(vrt_grid* g, const double* positions, const int64_t* nbr, int64_t ld);
+int grid_stencil(vrt_grid* g, const double k[3], double p, Stencil* st);
+
+// schedule.cu
+int schedule_build(vrt_grid* g, const double k[3], int down, int n_sweeps, double p, int prune, DirSchedule** out);
+DirSchedule* schedule_get(vrt_grid* g, const double k[3], int down, int n_sweeps, double p, int prune, int* rc);
+
+// sweep.cu
+struct SweepDir {
+    const DirSchedule* sch;
+    const double* alpha;     // [n][nlam]
+    double* I_main;          // [n][nlam]
+    double* scratch[MAX_SWEEPS];
+};
+struct SweepStats {
+    double kernels = 0, visits = 0, steps = 0, sweep_ms = 0;
+};
+// runs the merged sweep program of `nd` directions over nlam wavelengths; S is [n][ldS] (pointer at the chunk's first λ)
+int sweep_run(vrt_grid* g, int nd, const SweepDir* dirs, const double* S, int64_t ldS, int64_t nlam, cudaStream_t st, SweepStats* stats);
+int sweep_scratch_rows(const DirSchedule* sch, int s);
+
+// misc kernels (physics.cu)
+int permute_rows(const double* src, double* dst, const int32_t* map, int64_t n, int64_t nlam, int gather, cudaStream_t st);
+extern thread_local SweepStats g_last_stats;
+
+}  // namespace vrt
