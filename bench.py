@@ -1,0 +1,363 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the irregular-grid hot path: NLTE line Λ-iterations on a synthetic
+Bifrost-shaped Voronoi grid (BASELINE.json metric: cell·angle·freq updates/s per formal solution; s per NLTE
+Λ-iteration).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload nlte_1m|nlte_4m|nlte_16m|small] [--impl reference]
+
+A "step" is one full Λ-iteration (opacity + formal solution over all directions and wavelengths + source update
++ radiative rates + statistical equilibrium + criterion).  `value` = n_sites·n_dirs·n_λ / (time per step), inputs
+resident in HBM; `e2e` = the same through the C ABI with pinned HOST buffers (state in, S/J/populations out, every
+step).  N > 1 (torchrun): wavelengths are sharded over the ranks, one NCCL all-reduce of the radiative rates and one
+of the criterion per iteration; the total problem is fixed ("strong" scaling).
+--impl reference times the CPU oracle (a port of the reference's Julia algorithm; Julia itself is not installed)
+on a bounded sample of the same workload with all host threads.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (base sites tessellated by voro++, tiles in x, tiles in y, quadrature, nλ_bb, nλ_bf)
+    "small": (20000, 1, 1, "ul7n12", 50, 20),
+    "nlte_1m": (250000, 2, 2, "ul7n12", 50, 20),
+    "nlte_4m": (250000, 4, 4, "ul9n20", 50, 20),
+    "nlte_16m": (250000, 8, 8, "ul9n20", 50, 20),
+}
+
+
+def log(*a):
+    if int(os.environ.get("RANK", "0")) == 0:
+        print("[bench]", *a, file=sys.stderr, flush=True)
+
+
+def build_problem(workload):
+    """-> dict(pos, nbr, bounds, atm, n, quadrature path).  The base tessellation is cached under .vrt_cache/."""
+    from voronoirt_b200 import api, synth
+    base, kx, ky, qname, nbb, nbf = WORKLOADS[workload]
+    cache = os.environ.get("VRT_CACHE", os.path.join(ROOT, ".vrt_cache"))
+    os.makedirs(cache, exist_ok=True)
+    f = os.path.join(cache, f"base_{base}_seed2022.npz")
+    rank = int(os.environ.get("RANK", "0"))
+    if not os.path.exists(f):
+        if rank == 0:
+            t = time.time()
+            pos = synth.sample_sites(base, seed=2022)
+            nbr = synth.voronoi_neighbours(pos)
+            np.savez(f + ".tmp.npz", pos=pos, nbr=nbr.astype(np.int32))
+            os.replace(f + ".tmp.npz", f)
+            log(f"tessellated {base} base sites with voro++ in {time.time() - t:.1f}s")
+        else:
+            while not os.path.exists(f):
+                time.sleep(1.0)
+            time.sleep(1.0)
+    d = np.load(f)
+    pos, nbr = np.asfortranarray(d["pos"]), np.asfortranarray(d["nbr"].astype(np.int64))
+    atm = synth.atmosphere(pos[0], pos[1], pos[2])
+    bounds = dict(synth.BOX)
+    if kx * ky > 1:
+        pos, nbr, bounds = synth.tile_grid(pos, nbr, kx, ky)
+        atm = {k: np.tile(v, kx * ky) for k, v in atm.items()}
+    return dict(pos=pos, nbr=nbr, bounds=bounds, atm=atm, n=pos.shape[1], qpath=api.quadrature_path(qname), qname=qname,
+                nbb=nbb, nbf=nbf, tiles=(kx, ky), base=base)
+
+
+def shard_range(nlam, world, rank):
+    """contiguous balanced wavelength shards: the first nlam % world ranks get one more"""
+    q, r = divmod(nlam, world)
+    lo = rank * q + min(rank, r)
+    return lo, lo + q + (1 if rank < r else 0)
+
+
+class ClockSampler:
+    """samples nvidia-smi clocks and throttle reasons during the timed region"""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device = device
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.device)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            p = [x.strip() for x in r.split(",")]
+            if len(p) < 8:
+                continue
+            try:
+                sm.append(float(p[1])); mx.append(float(p[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak():
+    for p in (os.path.join(ROOT, "MEASURED_PEAKS.json"), "/root/repo/MEASURED_PEAKS.json"):
+        if os.path.exists(p):
+            try:
+                return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+            except Exception:
+                pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def cpu_reference_sample(P, line, inputs, threads, target_s=10.0, hoist=0):
+    """times the CPU oracle (port of the reference algorithm, threads over wavelengths like lambda_iteration.jl:91)
+    on a bounded sample: all directions x a contiguous block of wavelengths around the line centre."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle as O
+    from voronoirt_b200 import api, atom
+    lte, α_cont, ελ, Cr = inputs
+    atm = P["atm"]
+    b = P["bounds"]
+    bounds = [b["z_min"], b["z_max"], b["x_min"], b["x_max"], b["y_min"], b["y_max"]]
+    osites = O.Sites(np.ascontiguousarray(P["pos"].T), np.ascontiguousarray(P["nbr"].T), bounds)
+    sd = O.make_site_data(temperature=atm["temperature"], electron_density=atm["electron_density"], hydrogen_density=atm["hydrogen_density"],
+                          velocity_z=atm["velocity_z"], velocity_x=atm["velocity_x"], velocity_y=atm["velocity_y"], doppler_width=line.ΔD,
+                          alpha_cont=α_cont, destruction=ελ, C=np.ascontiguousarray(Cr.T), lte_pops=np.ascontiguousarray(lte.T))
+    w, th, ph, nq = api.read_quadrature(P["qpath"])
+    oq = O.make_quadrature(w, th, ph)
+    nlam = len(line.λ)
+    S = np.ascontiguousarray(atom.B_λ(line.λ[None, :], atm["temperature"][:, None]))
+    ls = line.as_struct()
+    nl = min(nlam, max(1, threads))
+    l0 = max(0, line.λidx[1] // 2 - nl // 2)
+
+    def run():
+        t = time.perf_counter()
+        O.J_lambda_voronoi(osites, ls, line.λ, sd, oq, S, lte.T, l0=l0, l1=l0 + nl, hoist=hoist)
+        return time.perf_counter() - t
+    return run, dict(nlam_sample=nl, l0=l0, ndirs=int(nq), n=P["n"], threads=O.num_threads())
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default=os.environ.get("VRT_WORKLOAD", "nlte_1m"), choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    W = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 0)
+    K = max(args.steps, 1)
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        from voronoirt_b200 import synth
+        P = build_problem(args.workload)
+        atm = P["atm"]
+        line, lte, α_cont, ελ, Cr = synth.line_inputs(atm["temperature"], atm["electron_density"], atm["hydrogen_density"], P["nbb"], P["nbf"])
+        threads = os.cpu_count() or 1
+        run, info = cpu_reference_sample(P, line, (lte, α_cont, ελ, Cr), threads)
+        for _ in range(min(W, 1)):
+            run()
+        ts = [run() for _ in range(K)]
+        t = float(np.mean(ts))
+        updates = info["n"] * info["ndirs"] * info["nlam_sample"]
+        val = updates / t
+        sample = (f"{info['nlam_sample']} of {len(line.λ)} wavelengths (index {info['l0']}..) x all {info['ndirs']} directions x {info['n']} sites, "
+                  "stencil recomputed at every visit like irregular_ray_tracing.jl:50; C/OpenMP port of the Julia reference (Julia not installed)")
+        out = {"impl": "reference", "metric": "cell*angle*freq updates/s per formal solution (NLTE Lambda-iteration)", "value": val,
+               "unit": "updates/s", "n_gpus": args.gpus, "steps": K, "warmup": min(W, 1), "ms_per_step": 1e3 * t, "higher_is_better": True,
+               "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+               "config": {"workload": workload_name(args.workload, P, len(line.λ)), "sites": P["n"], "quadrature": P["qname"], "n_lambda": len(line.λ)},
+               "cpu_baseline": {"value": val, "unit": "updates/s", "cores": info["threads"], "kind": "port", "sample": sample},
+               "e2e": {"value": val, "unit": "updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(out))
+        return 0
+
+    import torch
+    import voronoirt_b200 as V
+    from voronoirt_b200 import _lib, atom, synth
+    torch.cuda.set_device(local_rank)
+    _lib.check(_lib.lib().vrt_set_device(local_rank))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    t_setup = time.time()
+    P = build_problem(args.workload)
+    atm, b, n = P["atm"], P["bounds"], P["n"]
+    line, lte, α_cont, ελ, Cr = synth.line_inputs(atm["temperature"], atm["electron_density"], atm["hydrogen_density"], P["nbb"], P["nbf"])
+    nlam = len(line.λ)
+    lo, hi = shard_range(nlam, world, rank)
+    cell = V.read_cell(P["nbr"], n, P["pos"], b["x_min"], b["x_max"], b["y_min"], b["y_max"])
+    sites = V.VoronoiSites(*cell, atm["temperature"], atm["electron_density"], atm["hydrogen_density"], atm["velocity_z"],
+                           atm["velocity_x"], atm["velocity_y"], b["z_min"], b["z_max"], b["x_min"], b["x_max"], b["y_min"], b["y_max"], n)
+    w, th, ph, nq = V.read_quadrature(P["qpath"])
+    ndirs = int(np.sum(th != 90))
+    solver = V.Solver(sites, P["qpath"], line=line, α_cont=α_cont, ελ=ελ, C_rates=Cr, LTE_pops=lte,
+                      lam_range=(lo, hi) if world > 1 else None)
+    if world > 1:
+        class _Dev:
+            def __init__(self, ptr, count):
+                self.__cuda_array_interface__ = {"shape": (count,), "typestr": "<f8", "data": (ptr, False), "version": 3}
+
+        def allreduce(ptr, count, op):
+            t = torch.as_tensor(_Dev(ptr, count), device=torch.device("cuda", local_rank))
+            dist.all_reduce(t, op=dist.ReduceOp.MAX if op == 1 else dist.ReduceOp.SUM)
+            torch.cuda.synchronize()
+            return 0
+        solver.set_allreduce(allreduce)
+    log(f"setup {time.time() - t_setup:.1f}s: n={n} dirs={ndirs} nlam={nlam} shard=[{lo},{hi}) layers up/down={len(sites.layers_up) - 1}/{len(sites.layers_down) - 1}")
+
+    def sync():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- device-resident timing: state lives in HBM, K full Λ-iterations
+    solver.iterate(-1.0, W)
+    sync()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    res = solver.iterate(-1.0, K)
+    e1.record()
+    sync()
+    clocks = sampler.stop()
+    ms = e0.elapsed_time(e1)
+    stats = _lib.last_stats()
+    hist = res["history"]
+    tt = torch.tensor([ms, stats["sweep_ms"]], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    ms_max, sweep_ms_max = float(tt[0]), float(tt[1])
+    updates_total = float(n) * ndirs * nlam          # all ranks together, per step
+    value = updates_total / (ms_max / K / 1e3)
+
+    # ---- roofline of the dominant kernel (k_sweep): algorithmic bytes / measured kernel time (CUDA events in the library)
+    B_alg = 40.0 + 104.0 / nlam
+    local_updates = float(n) * ndirs * (hi - lo)
+    launches = max(stats["kernels"], 1)
+    achieved = B_alg * local_updates * K / (stats["sweep_ms"] / 1e3) / 1e9 if stats["sweep_ms"] > 0 else 0.0
+    peak, peak_src = measured_peak()
+    traffic = None
+    tf = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tf):
+        try:
+            traffic = json.load(open(tf)).get(args.workload)
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "kernel": "k_sweep", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_update": B_alg,
+                "sweep_ms_per_step": sweep_ms_max / K, "sweep_share_of_step": sweep_ms_max / ms_max,
+                "cell_visits_per_step": stats["visits"] / K * (1.0), "dependent_steps_per_step": stats["steps"] / K}
+
+    # ---- end to end through the C ABI with pinned host buffers: state in, one Λ-iteration, S/J/populations out
+    e2e = None
+    if not args.no_e2e:
+        nl = hi - lo
+        hS = torch.empty((n, nl), dtype=torch.float64).pin_memory()
+        hJ = torch.empty((n, nl), dtype=torch.float64).pin_memory()
+        hP = torch.empty((3, n), dtype=torch.float64).pin_memory()
+        S0, J0, p0 = solver.get_state()
+        hS.numpy()[:] = S0.T
+        hP.numpy()[:] = p0.T
+        import ctypes as C
+        L = _lib.lib()
+
+        def step():
+            _lib.check(L.vrt_set_state(solver.h, C.c_void_p(hS.data_ptr()), C.c_void_p(hP.data_ptr())))
+            _lib.check(L.vrt_lambda_iterate(solver.h, -1.0, 1, _abi_null_cb(), None, None))
+            _lib.check(L.vrt_get_state(solver.h, C.c_void_p(hS.data_ptr()), C.c_void_p(hJ.data_ptr()), C.c_void_p(hP.data_ptr())))
+        for _ in range(2):
+            step()
+        sync()
+        t0 = time.perf_counter()
+        for _ in range(K):
+            step()
+        sync()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt[0])
+        e2e = {"value": updates_total / (dt / K), "unit": "updates/s", "h2d_bytes_per_step": int(8 * (n * nl + 3 * n)),
+               "d2h_bytes_per_step": int(8 * (2 * n * nl + 3 * n)), "ms_per_step": 1e3 * dt / K,
+               "api": "vrt_set_state + vrt_lambda_iterate(1) + vrt_get_state with pinned host buffers"}
+
+    # ---- CPU baseline beside it (rank 0, N = 1 only): bounded sample of the same workload
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        run, info = cpu_reference_sample(P, line, (lte, α_cont, ελ, Cr), threads)
+        t = run()
+        cpu = {"value": info["n"] * info["ndirs"] * info["nlam_sample"] / t, "unit": "updates/s", "cores": info["threads"], "kind": "port",
+               "sample": f"{info['nlam_sample']} of {nlam} wavelengths x all {info['ndirs']} directions x {info['n']} sites, one formal solution "
+                         f"({t:.1f} s), stencil recomputed per visit like the reference; C/OpenMP port (Julia not installed)"}
+        run_h, _ = cpu_reference_sample(P, line, (lte, α_cont, ελ, Cr), threads, hoist=1)
+        th_ = run_h()
+        cpu["hoisted_value"] = info["n"] * info["ndirs"] * info["nlam_sample"] / th_
+
+    if rank == 0:
+        out = {"metric": "cell*angle*freq updates/s per formal solution (NLTE Lambda-iteration)", "value": value, "unit": "updates/s",
+               "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "strong",
+               "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+               "config": {"workload": workload_name(args.workload, P, nlam), "sites": n, "quadrature": P["qname"], "n_dirs": ndirs, "n_lambda": nlam,
+                          "parallelism": f"lambda-shard x{world}" if world > 1 else "single GPU", "l2_policy": "inputs larger than L2 "
+                          f"(S+J+I+alpha = {8 * n * nlam * (2 + 2 * ndirs) / 1e9:.1f} GB)", "n_sweeps": 3, "p": 7.0},
+               "s_per_lambda_iteration": ms_max / K / 1e3, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+               "gpu_launches": int(launches), "clocks": clocks,
+               "stage_ms": {k: float(np.mean([h[k] for h in hist])) for k in ("t_opacity_ms", "t_sweep_ms", "t_source_ms", "t_rates_ms", "t_stateq_ms", "t_total_ms")} if hist else None}
+        print(json.dumps(out))
+    solver.close()
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+def workload_name(key, P, nlam):
+    kx, ky = P["tiles"]
+    tile = f" (voro++ tessellation of {P['base']} sites tiled {kx}x{ky} periodically)" if kx * ky > 1 else ""
+    return f"{key}: NLTE line Lambda-iteration, {P['n']} Voronoi sites{tile}, {P['qname']}, {nlam} wavelengths, synthetic Bifrost-shaped atmosphere"
+
+
+def _abi_null_cb():
+    from voronoirt_b200 import _abi
+    import ctypes as C
+    return C.cast(None, _abi.vrt_iter_cb)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

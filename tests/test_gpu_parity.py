@@ -322,7 +322,7 @@ def test_wavelength_shards_sum_to_full_rates(V, oracle):
     for lo, hi in ((0, nl // 2), (nl // 2, nl)):
         sh = V.Solver(sites, qp, line=line, α_cont=P["α_cont"], ελ=P["ελ"], C_rates=P["C"], LTE_pops=P["lte"], lam_range=(lo, hi))
         Js = sh.mean_intensity(np.asfortranarray(S[lo:hi]), P["lte"])
-        assert np.array_equal(Js, Jf[lo:hi])
+        assert rel_err(Js, Jf[lo:hi]) < 1e-13   # wide and narrow rows run different kernels (TMA pipeline / register path)
         Rsum += sh.calculate_R(Js)
         sh.close()
     full.close()
@@ -343,7 +343,7 @@ def test_lambda_chunking_and_direction_batches_do_not_change_J(V, oracle, monkey
     b = V.Solver(sites, qp, line=line, α_cont=P["α_cont"], LTE_pops=P["lte"], lam_chunk=7)
     Jb = b.mean_intensity(S, P["lte"])
     b.close()
-    assert np.array_equal(Ja, Jb)   # same operations in the same order: bit-identical
+    assert rel_err(Jb, Ja) < 1e-13   # narrow chunks run the register-path kernel: same algorithm, different FMA contraction
     c = V.Solver(sites, qp, line=line, α_cont=P["α_cont"], LTE_pops=P["lte"], prune=0)
     Jc = c.mean_intensity(S, P["lte"])
     c.close()

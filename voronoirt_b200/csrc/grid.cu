@@ -478,7 +478,7 @@ int vrt_grid_get_schedule(vrt_grid* g, const double k[3], int32_t down, int32_t 
                           int32_t* cls, int32_t* sublevel, int32_t* stab, int64_t* n_steps, int64_t* n_visits) {
     if (!g || !k) return VRT_E_INVALID;
     int rc = VRT_OK;
-    DirSchedule* sch = schedule_get(g, k, down, n_sweeps, 7.0, prune, &rc);
+    DirSchedule* sch = schedule_get(g, k, down, n_sweeps, 7.0, prune, 1, &rc);
     if (!sch) return rc;
     const int64_t n = g->n;
     DevBuf<int32_t> tmp;

@@ -157,9 +157,39 @@ __device__ __forceinline__ uint32_t resolve(int32_t u, int t, const int32_t* __r
     return ((SEL_SCR0 + (uint32_t)(t - 1)) << SEL_SHIFT) | (uint32_t)slots[(int64_t)(t - 1) * n + u];
 }
 
-__global__ void k_build_visits(int64_t V, int64_t n, const uint32_t* __restrict__ val, const int32_t* __restrict__ up,
+// padded position of sorted visit i: every step is padded to a multiple of cv visits
+__device__ __forceinline__ int64_t padded_pos(int64_t i, uint32_t step, const int64_t* __restrict__ step_off,
+                                              const int64_t* __restrict__ pstep_off) {
+    return pstep_off[step] + (i - step_off[step]);
+}
+
+// vpos[voff[c] + s - 1] = padded position of visit (c, s)
+__global__ void k_visit_pos(int64_t V, const uint32_t* __restrict__ key, const uint32_t* __restrict__ val,
+                            const int64_t* __restrict__ voff, const int64_t* __restrict__ step_off,
+                            const int64_t* __restrict__ pstep_off, int32_t* __restrict__ vpos) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= V) return;
+    uint32_t v = val[i];
+    int s = (int)(v >> SEL_SHIFT);
+    int32_t c = (int32_t)(v & ROW_MASK);
+    vpos[voff[c] + s - 1] = (int32_t)padded_pos(i, key[i], step_off, pstep_off);
+}
+
+// chunk that produces the value of cell u at sweep t (t clipped to stab(u)); DEP_NONE for boundary / unprocessed cells
+__device__ __forceinline__ uint32_t producer(int32_t u, int t, const int32_t* __restrict__ stab, const int64_t* __restrict__ voff,
+                                             const int32_t* __restrict__ vpos, int cv) {
+    int su = stab[u];
+    if (su <= 0 || t <= 0) return DEP_NONE;
+    if (t > su) t = su;
+    return (uint32_t)(vpos[voff[u] + t - 1] / cv);
+}
+
+__global__ void k_build_visits(int64_t V, int64_t n, const uint32_t* __restrict__ key, const uint32_t* __restrict__ val,
+                               const int32_t* __restrict__ up,
                                const int32_t* __restrict__ cls, const int32_t* __restrict__ stab,
                                const int32_t* __restrict__ slots, const double* __restrict__ w, const double* __restrict__ r,
+                               const int64_t* __restrict__ voff, const int32_t* __restrict__ vpos,
+                               const int64_t* __restrict__ step_off, const int64_t* __restrict__ pstep_off, int cv,
                                Visit* __restrict__ out) {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= V) return;
@@ -170,22 +200,30 @@ __global__ void k_build_visits(int64_t V, int64_t n, const uint32_t* __restrict_
     o.cell = (uint32_t)c;
     o.dst = (s == stab[c]) ? ((SEL_MAIN << SEL_SHIFT) | (uint32_t)c)
                            : (((SEL_SCR0 + (uint32_t)(s - 1)) << SEL_SHIFT) | (uint32_t)slots[(int64_t)(s - 1) * n + c]);
-    uint32_t src[2], uu[2];
+    uint32_t src[2], uu[2], dep[2];
     for (int m = 0; m < 2; m++) {
         int32_t u = up[2 * c + m];
         int32_t k = cls[2 * c + m];
         uu[m] = u >= 0 ? (uint32_t)u : (uint32_t)c;
-        if (k == CLS_FINAL) src[m] = (SEL_MAIN << SEL_SHIFT) | (uint32_t)u;
-        else if (k == CLS_THIS) src[m] = resolve(u, s, stab, slots, n);
-        else if (k == CLS_LAG) src[m] = resolve(u, s - 1, stab, slots, n);
-        else src[m] = SEL_ZERO << SEL_SHIFT;
+        dep[m] = DEP_NONE;
+        if (k == CLS_FINAL) {
+            src[m] = (SEL_MAIN << SEL_SHIFT) | (uint32_t)u;
+            dep[m] = producer(u, MAX_SWEEPS, stab, voff, vpos, cv);
+        } else if (k == CLS_THIS) {
+            src[m] = resolve(u, s, stab, slots, n);
+            dep[m] = producer(u, s, stab, voff, vpos, cv);
+        } else if (k == CLS_LAG) {
+            src[m] = resolve(u, s - 1, stab, slots, n);
+            dep[m] = producer(u, s - 1, stab, voff, vpos, cv);
+        } else
+            src[m] = SEL_ZERO << SEL_SHIFT;
     }
     o.u1 = uu[0]; o.u2 = uu[1];
     o.src1 = src[0]; o.src2 = src[1];
-    o.pad0 = o.pad1 = 0;
+    o.dep1 = dep[0]; o.dep2 = dep[1];
     o.w1 = w[2 * c]; o.w2 = w[2 * c + 1];
     o.hr1 = 0.5 * r[2 * c]; o.hr2 = 0.5 * r[2 * c + 1];
-    out[i] = o;
+    out[padded_pos(i, key[i], step_off, pstep_off)] = o;
 }
 
 static int relax_loop(void (*launch)(void*), void* ctx, int* d_flag, int max_iter) {
@@ -201,7 +239,7 @@ static int relax_loop(void (*launch)(void*), void* ctx, int* d_flag, int max_ite
     return VRT_E_STATE;
 }
 
-int schedule_build(vrt_grid* g, const double k[3], int down, int n_sweeps, double p, int prune, DirSchedule** out) {
+int schedule_build(vrt_grid* g, const double k[3], int down, int n_sweeps, double p, int prune, int cv, DirSchedule** out) {
     *out = nullptr;
     if (n_sweeps < 1 || n_sweeps > MAX_SWEEPS - 1) {
         set_error("n_sweeps=%d unsupported (1..%d)", n_sweeps, MAX_SWEEPS - 1);
@@ -214,7 +252,7 @@ int schedule_build(vrt_grid* g, const double k[3], int down, int n_sweeps, doubl
     DirSchedule* sch = new DirSchedule();
     struct Guard { DirSchedule* s; ~Guard() { delete s; } } guard{sch};
     memcpy(sch->k, k, sizeof(double) * 3);
-    sch->down = down; sch->n_sweeps = n_sweeps; sch->p = p; sch->prune = prune;
+    sch->down = down; sch->n_sweeps = n_sweeps; sch->p = p; sch->prune = prune; sch->cv = cv;
 
     Stencil st;
     VRT_TRY(grid_stencil(g, k, p, &st));
@@ -331,13 +369,30 @@ int schedule_build(vrt_grid* g, const double k[3], int down, int n_sweeps, doubl
         DevBuf<char> stmp;
         VRT_TRY(stmp.alloc(sb));
         VRT_CUDA(cub::DeviceRadixSort::SortPairs(stmp.p, sb, key.p, key2.p, val.p, val2.p, (int)V, 0, bits));
-        DevBuf<int64_t> off;
-        VRT_TRY(off.alloc(T + 1));
+        DevBuf<int64_t> off, poff;
+        VRT_TRY(off.alloc(T + 1)); VRT_TRY(poff.alloc(T + 1));
         k_step_bounds<<<nblocks(V, bs), bs>>>(V, key2.p, off.p);
-        VRT_CUDA(cudaMemcpy(sch->step_off.data(), off.p, sizeof(int64_t) * T, cudaMemcpyDeviceToHost));
-        sch->step_off[T] = V;
-        VRT_TRY(sch->visits.alloc(V));
-        k_build_visits<<<nblocks(V, bs), bs>>>(V, n, val2.p, st.up.p, sch->cls.p, sch->stab.p, slots.p, st.w.p, st.r.p, sch->visits.p);
+        std::vector<int64_t> soff((size_t)T + 1, 0);
+        VRT_CUDA(cudaMemcpy(soff.data(), off.p, sizeof(int64_t) * T, cudaMemcpyDeviceToHost));
+        soff[T] = V;
+        VRT_CUDA(cudaMemcpy(off.p + T, &V, sizeof(int64_t), cudaMemcpyHostToDevice));
+        // pad every step to whole chunks of cv visits: a chunk never straddles two dependent steps
+        for (int64_t t = 0; t < T; t++) sch->step_off[t + 1] = sch->step_off[t] + (soff[t + 1] - soff[t] + cv - 1) / cv * cv;
+        const int64_t Vp = sch->step_off[T];
+        if (Vp >= (int64_t)INT32_MAX) {
+            set_error("too many visit slots (%lld) for one direction", (long long)Vp);
+            return VRT_E_INVALID;
+        }
+        VRT_CUDA(cudaMemcpy(poff.p, sch->step_off.data(), sizeof(int64_t) * (T + 1), cudaMemcpyHostToDevice));
+        sch->n_slots = Vp;
+        sch->n_chunks = Vp / cv;
+        DevBuf<int32_t> vpos;
+        VRT_TRY(vpos.alloc(V));
+        k_visit_pos<<<nblocks(V, bs), bs>>>(V, key2.p, val2.p, voff.p, off.p, poff.p, vpos.p);
+        VRT_TRY(sch->visits.alloc(Vp));
+        VRT_CUDA(cudaMemset(sch->visits.p, 0xff, sizeof(Visit) * (size_t)Vp));  // cell = CELL_DUMMY everywhere, then fill
+        k_build_visits<<<nblocks(V, bs), bs>>>(V, n, key2.p, val2.p, st.up.p, sch->cls.p, sch->stab.p, slots.p, st.w.p, st.r.p,
+                                               voff.p, vpos.p, off.p, poff.p, cv, sch->visits.p);
         VRT_CUDA(cudaGetLastError());
     }
     VRT_CUDA(cudaDeviceSynchronize());
@@ -346,15 +401,15 @@ int schedule_build(vrt_grid* g, const double k[3], int down, int n_sweeps, doubl
     return VRT_OK;
 }
 
-DirSchedule* schedule_get(vrt_grid* g, const double k[3], int down, int n_sweeps, double p, int prune, int* rc) {
+DirSchedule* schedule_get(vrt_grid* g, const double k[3], int down, int n_sweeps, double p, int prune, int cv, int* rc) {
     for (auto* s : g->cache)
         if (s->k[0] == k[0] && s->k[1] == k[1] && s->k[2] == k[2] && s->down == down && s->n_sweeps == n_sweeps &&
-            s->p == p && s->prune == prune) {
+            s->p == p && s->prune == prune && s->cv == cv) {
             *rc = VRT_OK;
             return s;
         }
     DirSchedule* s = nullptr;
-    *rc = schedule_build(g, k, down, n_sweeps, p, prune, &s);
+    *rc = schedule_build(g, k, down, n_sweeps, p, prune, cv, &s);
     if (*rc != VRT_OK) return nullptr;
     g->cache.push_back(s);
     return s;

@@ -437,7 +437,7 @@ struct vrt_solver {
 
 namespace vrt {
 
-static int solver_common_init(vrt_solver* s, vrt_grid* g, const vrt_quadrature* quad, const vrt_config* cfg) {
+static int solver_common_init(vrt_solver* s, vrt_grid* g, const vrt_quadrature* quad, const vrt_config* cfg, int64_t nlam_local) {
     s->g = g;
     s->n = g->n;
     vrt_config c;
@@ -451,6 +451,7 @@ static int solver_common_init(vrt_solver* s, vrt_grid* g, const vrt_quadrature* 
         if (c.p == 0.0) c.p = 7.0;
     }
     s->cfg = c;
+    const int cv = chunk_visits(c.lam_chunk > 0 ? std::min<int64_t>(c.lam_chunk, nlam_local) : nlam_local);
     if (!quad || quad->n_dirs <= 0 || !quad->weights || !quad->theta || !quad->phi) {
         set_error("solver: bad quadrature");
         return VRT_E_INVALID;
@@ -466,7 +467,7 @@ static int solver_common_init(vrt_solver* s, vrt_grid* g, const vrt_quadrature* 
         std::array<double, 3> k = {cos(t * PI / 180), cos(p * PI / 180) * sin(t * PI / 180), sin(p * PI / 180) * sin(t * PI / 180)};
         int down = !(t > 90);
         int rc = VRT_OK;
-        DirSchedule* sc = schedule_get(g, k.data(), down, c.n_sweeps, c.p, c.prune, &rc);
+        DirSchedule* sc = schedule_get(g, k.data(), down, c.n_sweeps, c.p, c.prune, cv, &rc);
         if (!sc) return rc;
         s->qk.push_back(k);
         s->qw.push_back(w[i]);
@@ -508,6 +509,8 @@ static int plan_buffers(vrt_solver* s) {
         rows_max = std::max(rows_max, per_dir_rows(d));
     }
     int64_t lc = s->cfg.lam_chunk > 0 ? std::min<int64_t>(s->cfg.lam_chunk, s->nlam) : s->nlam;
+    const char* envl = getenv("VRT_LAM_CHUNK");
+    if (envl && atoi(envl) > 0) lc = std::min<int64_t>(atoi(envl), s->nlam);
     int db = std::min(s->nd, MAX_DIRS);
     const char* env = getenv("VRT_MAX_DIRS");
     if (env && atoi(env) > 0) db = std::min(db, atoi(env));
@@ -534,18 +537,18 @@ static int plan_buffers(vrt_solver* s) {
             for (int k = 0; k < MAX_SWEEPS; k++) scr[k] = std::max(scr[k], s->sch[d]->scr_rows[k]);
         auto* bi = new DevBuf<double>();
         s->bufs.push_back(bi);
-        VRT_TRY(bi->alloc((size_t)n * lc));
+        VRT_TRY(bi->alloc((size_t)n * lc + 2));
         s->I_p[j] = bi->p;
         if (s->is_line) {
             auto* ba = new DevBuf<double>();
             s->bufs.push_back(ba);
-            VRT_TRY(ba->alloc((size_t)n * lc));
+            VRT_TRY(ba->alloc((size_t)n * lc + 2));
             s->alpha_p[j] = ba->p;
         }
         for (int k = 0; k < s->cfg.n_sweeps - 1; k++) {
             auto* bs = new DevBuf<double>();
             s->bufs.push_back(bs);
-            VRT_TRY(bs->alloc((size_t)std::max<int64_t>(scr[k], 1) * lc));
+            VRT_TRY(bs->alloc((size_t)std::max<int64_t>(scr[k], 1) * lc + 2));
             s->scr_p[j][k] = bs->p;
         }
     }
@@ -740,11 +743,11 @@ int vrt_formal_solve(vrt_grid* g, const double k[3], int32_t down, double p, int
     }
     const int64_t n = g->n;
     int rc = VRT_OK;
-    DirSchedule* sch = schedule_get(g, k, down ? 1 : 0, n_sweeps, p, 1, &rc);
+    DirSchedule* sch = schedule_get(g, k, down ? 1 : 0, n_sweeps, p, 1, chunk_visits(nlam), &rc);
     if (!sch) return rc;
     SweepStats stats;
     DevBuf<double> S_int, a_int, I_main, stage, scr[MAX_SWEEPS];
-    VRT_TRY(S_int.alloc((size_t)n * nlam)); VRT_TRY(a_int.alloc((size_t)n * nlam)); VRT_TRY(I_main.alloc((size_t)n * nlam));
+    VRT_TRY(S_int.alloc((size_t)n * nlam + 2)); VRT_TRY(a_int.alloc((size_t)n * nlam + 2)); VRT_TRY(I_main.alloc((size_t)n * nlam + 2));
     VRT_TRY(upload_rows(g, S, S_int.p, nlam, stage));
     VRT_TRY(upload_rows(g, alpha, a_int.p, nlam, stage));
     stats.kernels += 2;
@@ -754,7 +757,7 @@ int vrt_formal_solve(vrt_grid* g, const double k[3], int32_t down, double p, int
     dir.I_main = I_main.p;
     for (int s = 0; s < MAX_SWEEPS; s++) dir.scratch[s] = nullptr;
     for (int s = 0; s < n_sweeps - 1; s++) {
-        VRT_TRY(scr[s].alloc((size_t)std::max<int64_t>(sch->scr_rows[s], 1) * nlam));
+        VRT_TRY(scr[s].alloc((size_t)std::max<int64_t>(sch->scr_rows[s], 1) * nlam + 2));
         dir.scratch[s] = scr[s].p;
     }
     // I = zero(S); I[perm[1:n1]] = I_0 (irregular_ray_tracing.jl:23,33-35)
@@ -793,7 +796,11 @@ int vrt_solver_create_line(vrt_grid* g, const vrt_line* line, const double* lamb
     struct Guard { vrt_solver* s; ~Guard() { delete s; } } guard{s};
     s->is_line = 1;
     s->line = *line;
-    VRT_TRY(solver_common_init(s, g, quad, cfg));
+    {
+        int64_t nl = line->nlam;
+        if (cfg && cfg->lam_end > cfg->lam_begin) nl = cfg->lam_end - cfg->lam_begin;
+        VRT_TRY(solver_common_init(s, g, quad, cfg, nl));
+    }
     const int64_t n = g->n;
     s->nlam_total = line->nlam;
     if (line->nlam <= 0 || line->lidx[3] != line->nlam || line->lidx[0] != 0) {
@@ -835,7 +842,7 @@ int vrt_solver_create_line(vrt_grid* g, const vrt_line* line, const double* lamb
     if (sd->C) VRT_TRY(set_field(s, VRT_FIELD_C, sd->C));
     if (sd->lte_pops) VRT_TRY(set_field(s, VRT_FIELD_LTE_POPS, sd->lte_pops));
     VRT_TRY(s->gamma.alloc(n));
-    VRT_TRY(s->S.alloc((size_t)n * s->nlam)); VRT_TRY(s->J.alloc((size_t)n * s->nlam));
+    VRT_TRY(s->S.alloc((size_t)n * s->nlam + 2)); VRT_TRY(s->J.alloc((size_t)n * s->nlam));
     VRT_TRY(s->pops.alloc((size_t)3 * n)); VRT_TRY(s->Rp.alloc((size_t)6 * n));
     VRT_CUDA(cudaMemset(s->J.p, 0, sizeof(double) * (size_t)n * s->nlam));
 
@@ -895,7 +902,7 @@ int vrt_solver_create_continuum(vrt_grid* g, const double* alpha_cont, const dou
     vrt_solver* s = new vrt_solver();
     struct Guard { vrt_solver* s; ~Guard() { delete s; } } guard{s};
     s->is_line = 0;
-    VRT_TRY(solver_common_init(s, g, quad, cfg));
+    VRT_TRY(solver_common_init(s, g, quad, cfg, 1));
     const int64_t n = g->n;
     s->nlam_total = s->nlam = 1;
     s->l_begin = 0;
@@ -906,7 +913,7 @@ int vrt_solver_create_continuum(vrt_grid* g, const double* alpha_cont, const dou
     VRT_TRY(upload_site_vec(g, eps, s->eps, s->stage, "eps"));
     VRT_TRY(upload_site_vec(g, B0, s->B0, s->stage, "B0"));
     VRT_TRY(s->T.alloc(1));
-    VRT_TRY(s->S.alloc(n)); VRT_TRY(s->J.alloc(n));
+    VRT_TRY(s->S.alloc(n + 2)); VRT_TRY(s->J.alloc(n));
     VRT_CUDA(cudaMemset(s->J.p, 0, sizeof(double) * n));
     guard.s = nullptr;
     *out = s;

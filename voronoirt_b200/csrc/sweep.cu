@@ -2,13 +2,16 @@
 //
 // Replaces the hot loop of Delaunay_upII / Delaunay_downII (reference src/irregular_ray_tracing.jl:37-80,
 // :118-161).  The kernel interprets the sweep programs built by schedule.cu for up to MAX_DIRS
-// directions at once: a global step t runs the t-th dependent step of every direction, then all CTAs
-// meet at a grid barrier.  Inside a step the work is flat over (visit, wavelength) with the wavelength
-// innermost, so every gather of S, alpha and I of an upwind cell is a contiguous fp64 row read.
+// directions at once.  There is NO grid barrier: the merged program is one long topologically ordered list
+// of chunks (cv visits each); warp w owns chunks w, w+W, ... and a chunk only waits, by spinning on per-chunk
+// ready-flags, for the chunks that produce its two upwind intensities (sync-free SpTRSV style).  Inside a
+// chunk the work is flat over (visit, wavelength) with the wavelength innermost, so every gather of S, alpha
+// and I of an upwind cell is a contiguous fp64 row read.
 // Per item (irregular_ray_tracing.jl:54-77, functions.jl:392-395, :484-500):
 //     Δτ_m = r_m (α_c + α_um)/2 ;  (a,b,e) = linear_weights(Δτ_m)
 //     I_c  = 0 + w_1 (e_1 I_u1 + a_1 S_u1 + b_1 S_c) + w_2 (e_2 I_u2 + a_2 S_u2 + b_2 S_c)
 // Roofline: HBM-bound; algorithmic bytes per (cell,direction,wavelength) update are given in DESIGN.md.
+#include <stdlib.h>
 #include <algorithm>
 #include "vrt_internal.h"
 
@@ -19,35 +22,31 @@ struct DirDev {
     const double* alpha;
     double* I_main;
     double* scratch[MAX_SWEEPS];
+    int32_t* flags;          // one ready-flag per chunk of this direction's program (== epoch when done)
 };
 
 struct SweepParams {
     const DirDev* dirs;      // [nd] in global memory
-    const int32_t* goffT;    // [(T+1)][nd]: visit offset of direction d at global step t
+    const int32_t* goffT;    // [(T+1)][nd]: visit-slot offset of direction d at global step t (multiples of cv)
     const double* S;         // [n][ldS], first wavelength of the chunk
     int64_t ldS;             // row stride of S
-    unsigned int* barrier;   // grid barrier counter (zeroed before launch)
     int nd;
     int T;
     int nlam;
-    int cpw;                 // visits per warp chunk
+    int cv;                  // visits per chunk
+    int32_t epoch;
 };
 
-// linear_weights (functions.jl:484-500)
+// linear_weights (functions.jl:484-500), branch-free: the three branches are evaluated with selects so that a
+// warp whose lanes hold different wavelengths (very different Δτ) does not serialise them.
 __device__ __forceinline__ void linear_weights(double dtau, double& a, double& b, double& e) {
-    if (dtau < 5e-4) {
-        e = 1 - dtau + 0.5 * (dtau * dtau);
-        a = dtau * (1.0 / 2 - dtau / 3);
-        b = dtau * (1.0 / 2 - dtau / 6);
-    } else if (dtau > 50) {
-        e = 0.0;
-        a = 1 / dtau;
-        b = 1.0 - a;
-    } else {
-        e = exp(-dtau);
-        a = (1 - e) / dtau - e;
-        b = 1 - a - e;
-    }
+    const double ex = exp(-dtau);
+    const double inv = __drcp_rn(dtau);
+    const double a_mid = (1 - ex) * inv - ex;
+    const bool small = dtau < 5e-4, large = dtau > 50;
+    e = small ? (1 - dtau + 0.5 * (dtau * dtau)) : (large ? 0.0 : ex);
+    a = small ? dtau * (1.0 / 2 - dtau / 3) : (large ? inv : a_mid);
+    b = small ? dtau * (1.0 / 2 - dtau / 6) : (large ? 1.0 - inv : 1 - a_mid - ex);
 }
 
 __device__ __forceinline__ double load_I(uint32_t src, const DirDev* __restrict__ D, int nlam, int l) {
@@ -94,35 +93,43 @@ __device__ __forceinline__ void do_item(const VisitRegs& v, const DirDev* __rest
     base[(size_t)(dst & ROW_MASK) * nlam + l] = I;
 }
 
-__device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int target) {
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        atomicAdd(counter, 1u);
-        while (*(volatile unsigned int*)counter < target) {
-        }
-        __threadfence();
+// dataflow synchronisation (no grid barrier): a chunk spins on the ready-flags of the chunks that produce its
+// upwind intensities.  Chunks are claimed in a fixed global topological order (warp w owns chunks w, w+W, ...),
+// every warp of the cooperative launch is resident, so by induction on the chunk index no wait can deadlock.
+__device__ __forceinline__ void wait_flag(const int32_t* f, int32_t epoch) {
+    int v;
+    for (;;) {
+        asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+        if (v == epoch) break;
+        __nanosleep(40);
     }
-    __syncthreads();
+}
+__device__ __forceinline__ void set_flag(int32_t* f, int32_t epoch) {
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(f), "r"(epoch) : "memory");
 }
 
 constexpr int SWEEP_BLOCK = 256;
+#ifndef SWEEP_MIN_BLOCKS
+#define SWEEP_MIN_BLOCKS 3
+#endif
 
 template <bool SINGLE>
-__global__ void __launch_bounds__(SWEEP_BLOCK) k_sweep(const SweepParams P) {
+__global__ void __launch_bounds__(SWEEP_BLOCK, SWEEP_MIN_BLOCKS) k_sweep(const SweepParams P) {
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
-    const int warp_global = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
-    const int nwarps = (int)((gridDim.x * (unsigned)blockDim.x) >> 5);
-    const int nlam = P.nlam;
+    const long long nwarps = (long long)((gridDim.x * (unsigned)blockDim.x) >> 5);
+    long long gnext = (long long)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);  // next global chunk of this warp
+    long long base = 0;                                                                     // global index of step t's first chunk
+    const int nlam = P.nlam, cv = P.cv;
+    const int32_t epoch = P.epoch;
     const double* __restrict__ S = P.S;
     const int64_t ldS = P.ldS;
     for (int t = 0; t < P.T; t++) {
-        int beg = 0, end = 0, cnt = 0;
+        int beg = 0, cnt = 0;
         if (lane < P.nd) {
             beg = __ldg(P.goffT + (size_t)t * P.nd + lane);
-            end = __ldg(P.goffT + (size_t)(t + 1) * P.nd + lane);
-            cnt = (end - beg + P.cpw - 1) / P.cpw;
+            int end = __ldg(P.goffT + (size_t)(t + 1) * P.nd + lane);
+            cnt = (end - beg) / cv;
         }
         int incl = cnt;
 #pragma unroll
@@ -132,30 +139,265 @@ __global__ void __launch_bounds__(SWEEP_BLOCK) k_sweep(const SweepParams P) {
         }
         const int total = __shfl_sync(full, incl, 31);
         const int excl = incl - cnt;
-        for (int ch = warp_global; ch < total; ch += nwarps) {
+        while (gnext < base + total) {
+            const int ch = (int)(gnext - base);
             unsigned m = __ballot_sync(full, ch >= excl && ch < incl);
-            int d = __ffs(m) - 1;
-            int dbeg = __shfl_sync(full, beg, d);
-            int dend = __shfl_sync(full, end, d);
-            int dexcl = __shfl_sync(full, excl, d);
+            const int d = __ffs(m) - 1;
+            const int dbeg = __shfl_sync(full, beg, d);
+            const int dexcl = __shfl_sync(full, excl, d);
             const DirDev* __restrict__ D = P.dirs + d;
             const Visit* __restrict__ visits = D->visits;
-            int vb = dbeg + (ch - dexcl) * P.cpw;
+            const int cj = dbeg / cv + (ch - dexcl);   // chunk index inside direction d's program
+            int32_t* flags = D->flags;
             if (SINGLE) {
-                VisitRegs v = load_visit(visits + vb);
+                VisitRegs v = load_visit(visits + cj);
+                if (lane < 2) {
+                    uint32_t dep = lane ? v.b.w : v.b.z;
+                    if (dep != DEP_NONE) wait_flag(flags + dep, epoch);
+                }
+                __syncwarp();
                 for (int l = lane; l < nlam; l += 32) do_item(v, D, S, ldS, nlam, l);
             } else {
-                int ve = min(vb + P.cpw, dend);
-                int nitems = (ve - vb) * nlam;
+                const int vb = cj * cv;
+                for (int q = lane; q < 2 * cv; q += 32) {
+                    uint32_t dep = __ldg(reinterpret_cast<const uint32_t*>(visits + vb + (q >> 1)) + 6 + (q & 1));
+                    if (dep != DEP_NONE) wait_flag(flags + dep, epoch);
+                }
+                __syncwarp();
+                const int nitems = cv * nlam;
                 for (int i = lane; i < nitems; i += 32) {
                     int vi = i / nlam;
                     int l = i - vi * nlam;
                     VisitRegs v = load_visit(visits + vb + vi);
-                    do_item(v, D, S, ldS, nlam, l);
+                    if (v.a.x != CELL_DUMMY) do_item(v, D, S, ldS, nlam, l);
                 }
             }
+            __threadfence();   // every lane: its intensities are visible device-wide before the flag is
+            __syncwarp();
+            if (lane == 0) set_flag(flags + cj, epoch);
+            gnext += nwarps;
         }
-        grid_barrier(P.barrier, (unsigned)(t + 1) * gridDim.x);
+        base += total;
+    }
+}
+
+// ---------------------------------------------------------------- TMA-pipelined variant (wide rows)
+// One producer warp per CTA walks the CTA's chunks (CTA b owns global chunks b, b+B, ...), waits for the two
+// producer flags of a visit and then issues EIGHT 1-D bulk-tensor copies (cp.async.bulk, completion on an
+// mbarrier) that land the visit's rows  α_c S_c | α_u1 S_u1 I_u1 | α_u2 S_u2 I_u2  in a shared-memory stage.
+// NC consumer warps drain the stages: wavelengths across lanes, math in registers, result row written
+// straight to HBM, flag released, stage handed back.  The stage ring keeps tens of KB of gathers in flight
+// per SM independent of register pressure, which is what a latency-bound irregular gather needs.
+struct __align__(16) StageHdr {
+    double* dst;
+    int32_t* flag;
+    double w1, w2, hr1, hr2;
+    uint32_t offs;    // bit r: row r starts one double into its 16-byte aligned copy; bit 8+r: row r is all zero
+    uint32_t valid;
+    uint32_t seq;     // index of the chunk in this CTA's sequence: disambiguates mbarrier phases two rounds apart
+    uint32_t pad;
+};
+static_assert(sizeof(StageHdr) == 64, "StageHdr must be 64 bytes");
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done;
+    const uint32_t addr = smem_u32(bar);
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+constexpr int TMA_NC = 7;                         // consumer warps per CTA
+constexpr int TMA_BLOCK = 32 * (TMA_NC + 1);
+constexpr int TMA_MAX_STAGES = 32;
+
+__global__ void __launch_bounds__(TMA_BLOCK, 3) k_sweep_tma(const SweepParams P, int ns, int rowb) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem);
+    uint64_t* empty = full + TMA_MAX_STAGES;
+    StageHdr* hdr = reinterpret_cast<StageHdr*>(smem + 2 * TMA_MAX_STAGES * sizeof(uint64_t));
+    unsigned char* data = smem + 2 * TMA_MAX_STAGES * sizeof(uint64_t) + TMA_MAX_STAGES * sizeof(StageHdr);
+    const unsigned full_mask = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int nlam = P.nlam;
+    const int32_t epoch = P.epoch;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < ns; s++) {
+            mbar_init(full + s, 1);
+            mbar_init(empty + s, 1);
+            hdr[s].seq = 0xffffffffu;   // shared memory may still hold the headers of an earlier launch
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (warp == 0) {
+        // ===== producer: every lane owns one visit of a run of up to 32 consecutive chunks =====
+        // (the 32 visit records of a run are one coalesced 2 KB read; flags, stage hand-back and the eight bulk
+        //  copies of a visit are then handled by its lane, so up to 32 visits are being issued at once)
+        long long rnext = blockIdx.x;     // next global run of this CTA (CTA b owns runs b, b+B, ...)
+        long long rbase = 0;              // global index of step t's first run
+        const long long nblk = gridDim.x;
+        unsigned it = 0;                  // chunks handed to the consumers so far
+        // a run never exceeds the ring: per stage at most one refill may be pending, otherwise the parity wait on
+        // the `empty` barrier could be satisfied by the wrong phase
+        const int RL = min(32, ns);
+        const double* __restrict__ S = P.S;
+        const int64_t ldS = P.ldS;
+        for (int t = 0; t < P.T; t++) {
+            int beg = 0, len = 0, cnt = 0;
+            if (lane < P.nd) {
+                beg = __ldg(P.goffT + (size_t)t * P.nd + lane);
+                len = __ldg(P.goffT + (size_t)(t + 1) * P.nd + lane) - beg;
+                cnt = (len + RL - 1) / RL;    // runs of this direction in this step
+            }
+            int incl = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int v = __shfl_up_sync(full_mask, incl, o);
+                if (lane >= o) incl += v;
+            }
+            const int total = __shfl_sync(full_mask, incl, 31);
+            const int excl = incl - cnt;
+            while (rnext < rbase + total) {
+                const int run = (int)(rnext - rbase);
+                unsigned m = __ballot_sync(full_mask, run >= excl && run < incl);
+                const int d = __ffs(m) - 1;
+                const int r_in_dir = run - __shfl_sync(full_mask, excl, d);
+                const int dbeg = __shfl_sync(full_mask, beg, d);
+                const int dlen = __shfl_sync(full_mask, len, d);
+                const int first = r_in_dir * RL;
+                const int nrun = min(RL, dlen - first);       // chunks in this run
+                const DirDev* __restrict__ D = P.dirs + d;
+                if (lane < nrun) {
+                    const int cj = dbeg + first + lane;
+                    const VisitRegs v = load_visit(D->visits + cj);
+                    const unsigned my = it + (unsigned)lane;
+                    const int stage = (int)(my % (unsigned)ns);
+                    const uint32_t par = (my / (unsigned)ns) & 1u;
+                    if (v.b.z != DEP_NONE) wait_flag(D->flags + v.b.z, epoch);
+                    if (v.b.w != DEP_NONE) wait_flag(D->flags + v.b.w, epoch);
+                    mbar_wait(empty + stage, par ^ 1u);
+                    // rows of the stage: 0 α_c, 1 S_c, 2 α_u1, 3 S_u1, 4 I_u1, 5 α_u2, 6 S_u2, 7 I_u2
+                    const double* src[8];
+                    const double* alpha = D->alpha;
+                    src[0] = alpha + (size_t)v.a.x * nlam;
+                    src[1] = S + (size_t)v.a.x * ldS;
+                    src[2] = alpha + (size_t)v.a.z * nlam;
+                    src[3] = S + (size_t)v.a.z * ldS;
+                    src[5] = alpha + (size_t)v.a.w * nlam;
+                    src[6] = S + (size_t)v.a.w * ldS;
+                    {
+                        const uint32_t s1 = v.b.x >> SEL_SHIFT, s2 = v.b.y >> SEL_SHIFT;
+                        src[4] = s1 == SEL_ZERO ? nullptr : (s1 == SEL_MAIN ? D->I_main : D->scratch[s1 - SEL_SCR0]) + (size_t)(v.b.x & ROW_MASK) * nlam;
+                        src[7] = s2 == SEL_ZERO ? nullptr : (s2 == SEL_MAIN ? D->I_main : D->scratch[s2 - SEL_SCR0]) + (size_t)(v.b.y & ROW_MASK) * nlam;
+                    }
+                    uint32_t offmask = 0, zeromask = 0, tot = 0;
+#pragma unroll
+                    for (int r = 0; r < 8; r++) {
+                        if (src[r]) {
+                            const uint32_t off = (uint32_t)((reinterpret_cast<uintptr_t>(src[r]) >> 3) & 1u);
+                            offmask |= off << r;
+                            tot += (uint32_t)(((nlam + off) * 8 + 15) & ~15);
+                        } else
+                            zeromask |= 1u << r;
+                    }
+                    StageHdr h;
+                    const uint32_t dsel = v.a.y >> SEL_SHIFT;
+                    h.dst = (dsel == SEL_MAIN ? D->I_main : D->scratch[dsel - SEL_SCR0]) + (size_t)(v.a.y & ROW_MASK) * nlam;
+                    h.flag = D->flags + cj;
+                    h.w1 = v.w.x; h.w2 = v.w.y; h.hr1 = v.hr.x; h.hr2 = v.hr.y;
+                    h.offs = offmask | (zeromask << 8);
+                    h.valid = 1;
+                    h.seq = my;
+                    h.pad = 0;
+                    hdr[stage] = h;
+                    mbar_arrive_expect_tx(full + stage, tot);
+                    asm volatile("fence.proxy.async;" ::: "memory");   // the flags were acquired through the generic proxy
+#pragma unroll
+                    for (int r = 0; r < 8; r++) {
+                        if (src[r]) {
+                            const uint32_t off = (offmask >> r) & 1u;
+                            bulk_g2s(data + (size_t)(stage * 8 + r) * rowb, src[r] - off, (uint32_t)(((nlam + off) * 8 + 15) & ~15), full + stage);
+                        }
+                    }
+                }
+                __syncwarp();
+                it += (unsigned)nrun;
+                rnext += nblk;
+            }
+            rbase += total;
+        }
+        // one termination token per consumer warp
+        for (int k = 0; k < TMA_NC; k++) {
+            const int stage = (int)(it % (unsigned)ns);
+            const uint32_t par = (it / (unsigned)ns) & 1u;
+            if (lane == 0) {
+                mbar_wait(empty + stage, par ^ 1u);
+                hdr[stage].valid = 0;
+                hdr[stage].seq = it;
+                mbar_arrive(full + stage);
+            }
+            __syncwarp();
+            it++;
+        }
+    } else {
+        // ===== consumers =====
+        for (unsigned it = (unsigned)(warp - 1);; it += TMA_NC) {
+            const int stage = (int)(it % (unsigned)ns);
+            const uint32_t par = (it / (unsigned)ns) & 1u;
+            // producer lanes fill stages out of order, so a parity wait alone could be satisfied by the fill of two
+            // rounds ago; the sequence number in the header tells the rounds apart
+            for (;;) {
+                mbar_wait(full + stage, par);
+                if (reinterpret_cast<volatile StageHdr*>(hdr)[stage].seq == it) break;
+                __nanosleep(64);
+            }
+            const StageHdr h = hdr[stage];
+            if (!h.valid) break;
+            const unsigned char* rb = data + (size_t)stage * 8 * rowb;
+            const double* r0 = reinterpret_cast<const double*>(rb) + (h.offs & 1u);
+            const double* r1 = reinterpret_cast<const double*>(rb + rowb) + ((h.offs >> 1) & 1u);
+            const double* r2 = reinterpret_cast<const double*>(rb + 2 * rowb) + ((h.offs >> 2) & 1u);
+            const double* r3 = reinterpret_cast<const double*>(rb + 3 * rowb) + ((h.offs >> 3) & 1u);
+            const double* r4 = reinterpret_cast<const double*>(rb + 4 * rowb) + ((h.offs >> 4) & 1u);
+            const double* r5 = reinterpret_cast<const double*>(rb + 5 * rowb) + ((h.offs >> 5) & 1u);
+            const double* r6 = reinterpret_cast<const double*>(rb + 6 * rowb) + ((h.offs >> 6) & 1u);
+            const double* r7 = reinterpret_cast<const double*>(rb + 7 * rowb) + ((h.offs >> 7) & 1u);
+            const bool z1 = (h.offs >> 12) & 1u, z2 = (h.offs >> 15) & 1u;
+            for (int l = lane; l < nlam; l += 32) {
+                const double a_c = r0[l], S_c = r1[l];
+                const double I_1 = z1 ? 0.0 : r4[l];
+                const double I_2 = z2 ? 0.0 : r7[l];
+                double a, b, e;
+                linear_weights(h.hr1 * (a_c + r2[l]), a, b, e);
+                double I = 0.0 + (e * I_1 + a * r3[l] + b * S_c) * h.w1;
+                linear_weights(h.hr2 * (a_c + r5[l]), a, b, e);
+                I += (e * I_2 + a * r6[l] + b * S_c) * h.w2;
+                h.dst[l] = I;
+            }
+            __threadfence();
+            __syncwarp();
+            if (lane == 0) {
+                set_flag(h.flag, epoch);
+                mbar_arrive(empty + stage);
+            }
+        }
     }
 }
 
@@ -215,8 +457,27 @@ int sweep_run(vrt_grid* g, int nd, const SweepDir* dirs, const double* S, int64_
     }
     if (T == 0) return VRT_OK;
 
-    std::vector<DirDev> hd(nd);
+    // ready-flags: one int per chunk, carved from a pool that is never cleared (flag == epoch <=> done now)
+    const int cv = dirs[0].sch->cv;
+    size_t nflags = 0;
     for (int d = 0; d < nd; d++) {
+        if (dirs[d].sch->cv != cv) {
+            set_error("sweep_run: schedules of one launch must share the chunk size");
+            return VRT_E_INVALID;
+        }
+        nflags += (size_t)dirs[d].sch->n_chunks;
+    }
+    if (g->flag_pool.n < nflags || g->epoch >= INT32_MAX - 1) {
+        VRT_TRY(g->flag_pool.alloc(nflags));
+        VRT_CUDA(cudaMemsetAsync(g->flag_pool.p, 0, sizeof(int32_t) * g->flag_pool.n, st));
+        g->epoch = 0;
+    }
+    const int32_t epoch = ++g->epoch;
+    std::vector<DirDev> hd(nd);
+    size_t fo = 0;
+    for (int d = 0; d < nd; d++) {
+        hd[d].flags = g->flag_pool.p + fo;
+        fo += (size_t)dirs[d].sch->n_chunks;
         hd[d].visits = dirs[d].sch->visits.p;
         hd[d].alpha = dirs[d].alpha;
         hd[d].I_main = dirs[d].I_main;
@@ -224,43 +485,58 @@ int sweep_run(vrt_grid* g, int nd, const SweepDir* dirs, const double* S, int64_
     }
     DevBuf<DirDev> d_dirs;
     DevBuf<int32_t> d_goffT;
-    DevBuf<unsigned int> d_bar;
-    VRT_TRY(d_dirs.alloc(nd)); VRT_TRY(d_goffT.alloc(goffT.size())); VRT_TRY(d_bar.alloc(1));
+    VRT_TRY(d_dirs.alloc(nd)); VRT_TRY(d_goffT.alloc(goffT.size()));
     VRT_CUDA(cudaMemcpyAsync(d_dirs.p, hd.data(), sizeof(DirDev) * nd, cudaMemcpyHostToDevice, st));
     VRT_CUDA(cudaMemcpyAsync(d_goffT.p, goffT.data(), sizeof(int32_t) * goffT.size(), cudaMemcpyHostToDevice, st));
-    VRT_CUDA(cudaMemsetAsync(d_bar.p, 0, sizeof(unsigned int), st));
 
     SweepParams P;
     P.dirs = d_dirs.p;
     P.goffT = d_goffT.p;
     P.S = S;
     P.ldS = ldS;
-    P.barrier = d_bar.p;
     P.nd = nd;
     P.T = T;
     P.nlam = (int)nlam;
-    P.cpw = nlam >= 48 ? 1 : (int)((64 + nlam - 1) / nlam);
+    P.cv = cv;
+    P.epoch = epoch;
 
     int dev = 0, sms = 0, per_sm = 0;
     VRT_CUDA(cudaGetDevice(&dev));
     VRT_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    const void* fn = P.cpw == 1 ? (const void*)k_sweep<true> : (const void*)k_sweep<false>;
-    VRT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, SWEEP_BLOCK, 0));
+    const char* env_tma = getenv("VRT_TMA");
+    const bool use_tma = P.cv == 1 && nlam >= 16 && !(env_tma && atoi(env_tma) == 0);
+    const void* fn;
+    int block, ns = 0, rowb = 0;
+    size_t shmem = 0;
+    if (use_tma) {
+        fn = (const void*)k_sweep_tma;
+        block = TMA_BLOCK;
+        rowb = (int)(((nlam + 1) * 8 + 15) & ~15);
+        const size_t fixed = 2 * TMA_MAX_STAGES * sizeof(uint64_t) + TMA_MAX_STAGES * sizeof(StageHdr);
+        const char* env_ns = getenv("VRT_TMA_STAGES");
+        const char* env_kb = getenv("VRT_TMA_SMEM_KB");
+        const size_t budget = (size_t)(env_kb && atoi(env_kb) > 0 ? atoi(env_kb) : 72) * 1024;
+        ns = (int)((budget - fixed) / ((size_t)8 * rowb));
+        if (env_ns && atoi(env_ns) > 0) ns = atoi(env_ns);
+        ns = std::max(2, std::min(ns, TMA_MAX_STAGES));
+        shmem = fixed + (size_t)ns * 8 * rowb;
+        VRT_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
+    } else {
+        fn = P.cv == 1 ? (const void*)k_sweep<true> : (const void*)k_sweep<false>;
+        block = SWEEP_BLOCK;
+    }
+    VRT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, block, shmem));
     if (per_sm < 1) {
         set_error("sweep kernel cannot be resident");
         return VRT_E_CUDA;
     }
     int grid = sms * per_sm;
-    if ((double)T * grid >= 4.0e9) {
-        set_error("sweep program too long for the 32-bit barrier counter");
-        return VRT_E_INVALID;
-    }
     cudaEvent_t e0, e1;
     VRT_CUDA(cudaEventCreate(&e0));
     VRT_CUDA(cudaEventCreate(&e1));
     VRT_CUDA(cudaEventRecord(e0, st));
-    void* args[] = {(void*)&P};
-    cudaError_t le = cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(SWEEP_BLOCK), args, 0, st);
+    void* args[] = {(void*)&P, (void*)&ns, (void*)&rowb};
+    cudaError_t le = cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(block), args, shmem, st);
     if (le != cudaSuccess) {
         cudaEventDestroy(e0);
         cudaEventDestroy(e1);

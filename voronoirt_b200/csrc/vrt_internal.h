@@ -72,6 +72,8 @@ constexpr uint32_t SEL_SHIFT = 29;
 constexpr uint32_t ROW_MASK = (1u << SEL_SHIFT) - 1u;
 constexpr int MAX_SWEEPS = 6;            // scratch selectors 2..6 -> sweeps 1..5 non-final
 constexpr int MAX_DIRS = 32;             // directions merged into one sweep launch
+constexpr uint32_t DEP_NONE = 0xffffffffu;   // operand needs no producer (boundary value, zero, or never-processed site)
+constexpr uint32_t CELL_DUMMY = 0xffffffffu; // padding visit (steps are padded to whole chunks)
 
 // reference classes (SURVEY App. G rule 2)
 enum : int32_t { CLS_FINAL = 0, CLS_THIS = 1, CLS_LAG = 2, CLS_ZERO = 3 };
@@ -81,7 +83,7 @@ struct __align__(16) Visit {
     uint32_t dst;    // selector|row the result is written to
     uint32_t u1, u2; // rows of S / alpha of the two upwind cells
     uint32_t src1, src2;  // selector|row the upwind intensities are read from
-    uint32_t pad0, pad1;
+    uint32_t dep1, dep2;  // chunk (of this direction's program) that produces src1 / src2, or DEP_NONE
     double w1, w2;   // dot_weights (irregular_ray_tracing.jl:51)
     double hr1, hr2; // r/2 (euclidean, :66; the /2 of trapezoidal, functions.jl:393)
 };
@@ -101,9 +103,12 @@ struct DirSchedule {
     int n_sweeps = 3;
     int prune = 1;
     double p = 7.0;
-    DevBuf<Visit> visits;           // V records sorted by local step
-    int64_t n_visits = 0;
-    std::vector<int64_t> step_off;  // local steps: T_local+1 offsets into visits
+    int cv = 1;                     // visits per chunk (work unit of one warp; one ready-flag per chunk)
+    DevBuf<Visit> visits;           // n_slots records sorted by local step, every step padded to a multiple of cv
+    int64_t n_visits = 0;           // real (non-padding) visits
+    int64_t n_slots = 0;            // padded length = n_chunks * cv
+    int64_t n_chunks = 0;
+    std::vector<int64_t> step_off;  // local steps: T_local+1 offsets into visits (padded positions)
     // (layer, sweep) -> number of sub-levels; index (layer-2)*n_sweeps + (sweep-1)
     std::vector<int32_t> nsub;
     int64_t scr_rows[MAX_SWEEPS] = {0};  // rows needed in scratch buffer s (sweep s+1 non-final writers)
@@ -133,8 +138,11 @@ struct vrt_grid {
     vrt::DevBuf<int32_t> layer_dn;   // n
     vrt::DevBuf<int32_t> rank_dn;    // n: 0-based rank in perm_down of internal cell
     vrt::DevBuf<int32_t> perm_dn_int;// n: rank in perm_down -> internal id
-    // cached schedules (keyed by direction, down, n_sweeps, p, prune)
+    // cached schedules (keyed by direction, down, n_sweeps, p, prune, cv)
     std::vector<vrt::DirSchedule*> cache;
+    // ready-flags of the dataflow sweep: flag == epoch <=> chunk done in the current launch (no memset per launch)
+    vrt::DevBuf<int32_t> flag_pool;
+    int32_t epoch = 0;
     ~vrt_grid();
 };
 
@@ -145,8 +153,10 @@ int grid_build(vrt_grid* g, const double* positions, const int64_t* nbr, int64_t
 int grid_stencil(vrt_grid* g, const double k[3], double p, Stencil* st);
 
 // schedule.cu
-int schedule_build(vrt_grid* g, const double k[3], int down, int n_sweeps, double p, int prune, DirSchedule** out);
-DirSchedule* schedule_get(vrt_grid* g, const double k[3], int down, int n_sweeps, double p, int prune, int* rc);
+int schedule_build(vrt_grid* g, const double k[3], int down, int n_sweeps, double p, int prune, int cv, DirSchedule** out);
+DirSchedule* schedule_get(vrt_grid* g, const double k[3], int down, int n_sweeps, double p, int prune, int cv, int* rc);
+// visits per chunk for rows of nlam wavelengths
+inline int chunk_visits(int64_t nlam) { return nlam >= 16 ? 1 : (nlam >= 24 ? 2 : (nlam >= 12 ? 4 : (nlam >= 6 ? 8 : (nlam >= 3 ? 16 : 32)))); }
 
 // sweep.cu
 struct SweepDir {

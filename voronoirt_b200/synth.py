@@ -154,3 +154,38 @@ def continuum_inputs(T, ne, NH):
     α_a = 1.0e-26 * NH * np.clip(T / 6000.0, 0.2, 5.0) ** 2
     α_cont = α_s + α_a
     return α_cont, α_a / α_cont, atom.B_λ(500.0, T)
+
+
+def tile_grid(pos, nbr, kx, ky, bounds=None):
+    """Replicate a grid that is periodic in x and y into a kx x ky times larger periodic box.
+
+    The Voronoi tessellation of the replicated point set is exactly the replicated tessellation, so the
+    neighbour lists (and their order) carry over; only the tile of each neighbour has to be found, from the
+    nearest periodic image.  Used to reach benchmark sizes (1 M - 16 M sites) from a base grid that the
+    single-threaded voro++ driver can tessellate in seconds.  -> (positions (3, n), NeighbourMatrix (n, ld), bounds dict)
+    """
+    b = dict(bounds or BOX)
+    n0, ld = nbr.shape
+    Lx, Ly = b["x_max"] - b["x_min"], b["y_max"] - b["y_min"]
+    x, y = pos[1], pos[2]
+    ids = nbr[:, 1:]
+    valid = ids > 0
+    j = np.where(valid, ids - 1, 0)
+    sx = np.where(valid, np.rint((x[:, None] - x[j]) / Lx), 0).astype(np.int64)
+    sy = np.where(valid, np.rint((y[:, None] - y[j]) / Ly), 0).astype(np.int64)
+    n = n0 * kx * ky
+    out_pos = np.empty((3, n), order="F")
+    out_nbr = np.zeros((n, ld), dtype=np.int64, order="F")
+    for a in range(kx):
+        for c in range(ky):
+            t = a * ky + c
+            sl = slice(t * n0, (t + 1) * n0)
+            out_pos[0, sl] = pos[0]
+            out_pos[1, sl] = x + a * Lx
+            out_pos[2, sl] = y + c * Ly
+            tt = ((a + sx) % kx) * ky + ((c + sy) % ky)
+            out_nbr[sl, 0] = nbr[:, 0]
+            out_nbr[sl, 1:] = np.where(valid, ids + tt * n0, ids)
+    b["x_max"] = b["x_min"] + kx * Lx
+    b["y_max"] = b["y_min"] + ky * Ly
+    return out_pos, out_nbr, b
