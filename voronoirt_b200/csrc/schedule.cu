@@ -8,10 +8,11 @@
 //   2. chg[s][c] = "the value of c computed in sweep s can differ from sweep s-1" (structural, exact):
 //      chg[1] = processed; chg[s] = OR_LAG chg[s-1][u]  OR_THIS chg[s][u].  stab(c) = #s with chg[s][c].
 //      With prune=0 every processed cell is visited n_sweeps times like the reference does;
-//   3. sub-levels per sweep over the active cells: sub_s(c) = 1 + max sub_s(u) over active THIS refs;
-//   4. a VISIT per (c, s <= stab(c)), sorted by step = (layer, sweep, sub-level); all operands are
-//      resolved to (buffer,row): sweep-s values of cells with stab > s live in scratch buffer s, the final
-//      value in the main intensity array, so there is no write-after-read hazard between sweeps.
+//   3. a VISIT per (c, s <= stab(c)); every operand is resolved to (buffer,row): sweep-s values of cells with
+//      stab > s live in scratch buffer s, the final value in the main intensity array, so no value is ever
+//      overwritten and ANY topological order of the visits reproduces the sequential result;
+//   4. the visits are ordered by their level in the dependency DAG (level = 1 + deepest producer read) and
+//      chunked; each chunk records the chunks that produce its two upwind intensities (dataflow sweep).
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 #include <string.h>
@@ -118,6 +119,51 @@ __global__ void k_nsub(int64_t n, const int32_t* __restrict__ layer, const int32
     if (v > 0) atomicMax(&nsub[(layer[c] - 2) * n_sweeps + (s - 1)], v);
 }
 
+// DAG level of every visit (c, s <= stab(c)): 1 + the deepest producer it reads.  Jacobi relaxation to the
+// longest-path fixed point (levels only grow).  lev is [S][n]; the producer rules are those of producer() below.
+__global__ void k_level_relax(int64_t n, int S, const int32_t* __restrict__ up, const int32_t* __restrict__ cls,
+                              const int32_t* __restrict__ stab, int32_t* lev, int* __restrict__ changed) {
+    int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (c >= n) return;
+    const int st = stab[c];
+    bool ch = false;
+    for (int s = 1; s <= st; s++) {
+        int32_t want = 1;
+        for (int m = 0; m < 2; m++) {
+            const int32_t k = cls[2 * c + m];
+            if (k != CLS_FINAL && k != CLS_THIS && k != CLS_LAG) continue;
+            const int32_t u = up[2 * c + m];
+            const int su = stab[u];
+            int t = k == CLS_FINAL ? su : (k == CLS_THIS ? s : s - 1);
+            if (su <= 0 || t <= 0) continue;
+            if (t > su) t = su;
+            const int32_t lu = ((volatile int32_t*)lev)[(int64_t)(t - 1) * n + u] + 1;
+            want = lu > want ? lu : want;
+        }
+        int32_t* p = lev + (int64_t)(s - 1) * n + c;
+        if (want > *p) {
+            *p = want;
+            ch = true;
+        }
+    }
+    if (ch) *changed = 1;
+}
+
+__global__ void k_level_init(int64_t n, int S, const int32_t* __restrict__ stab, int32_t* __restrict__ lev) {
+    int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (c >= n) return;
+    for (int s = 1; s <= S; s++) lev[(int64_t)(s - 1) * n + c] = s <= stab[c] ? 1 : 0;
+}
+
+__global__ void k_level_max(int64_t n, int S, const int32_t* __restrict__ lev, int32_t* __restrict__ out) {
+    int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    int32_t m = 0;
+    if (c < n)
+        for (int s = 0; s < S; s++) m = max(m, lev[(int64_t)s * n + c]);
+    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m > 0) atomicMax(out, m);
+}
+
 __global__ void k_stab_acc(int64_t n, const uint8_t* __restrict__ chg, int32_t* __restrict__ stab, int first) {
     int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (c < n) stab[c] = (first ? 0 : stab[c]) + (chg[c] ? 1 : 0);
@@ -129,16 +175,14 @@ __global__ void k_flag_gt(int64_t n, const int32_t* __restrict__ stab, int s, in
 }
 
 // emit (key = local step, val = sweep<<29 | cell) for every visit, in cell order
-__global__ void k_emit(int64_t n, const int32_t* __restrict__ layer, const int32_t* __restrict__ stab,
-                       const int64_t* __restrict__ voff, const int32_t* __restrict__ sub_all /* [s][n] */,
-                       const int32_t* __restrict__ stepbase /* [(layer-2)*S + s-1] */, int n_sweeps,
-                       uint32_t* __restrict__ key, uint32_t* __restrict__ val) {
+__global__ void k_emit(int64_t n, const int32_t* __restrict__ stab, const int64_t* __restrict__ voff,
+                       const int32_t* __restrict__ lev /* [s][n] */, uint32_t* __restrict__ key, uint32_t* __restrict__ val) {
     int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (c >= n) return;
     int32_t st = stab[c];
     int64_t o = voff[c];
     for (int s = 1; s <= st; s++) {
-        int32_t t = stepbase[(layer[c] - 2) * n_sweeps + (s - 1)] + sub_all[(int64_t)(s - 1) * n + c] - 1;
+        int32_t t = lev[(int64_t)(s - 1) * n + c] - 1;
         key[o + s - 1] = (uint32_t)t;
         val[o + s - 1] = ((uint32_t)s << SEL_SHIFT) | (uint32_t)c;
     }
@@ -248,7 +292,6 @@ int schedule_build(vrt_grid* g, const double k[3], int down, int n_sweeps, doubl
     const int64_t n = g->n;
     const int bs = 256;
     const int nb = nblocks(n, bs);
-    const int64_t L = down ? g->L_down : g->L_up;
     DirSchedule* sch = new DirSchedule();
     struct Guard { DirSchedule* s; ~Guard() { delete s; } } guard{sch};
     memcpy(sch->k, k, sizeof(double) * 3);
@@ -283,12 +326,9 @@ int schedule_build(vrt_grid* g, const double k[3], int down, int n_sweeps, doubl
     }
 
     const int S = n_sweeps;
-    const int64_t nls = (L >= 2 ? (L - 1) : 0) * S;  // (layer 2..L) x sweeps
     DevBuf<uint8_t> chg;      // [S][n]
-    DevBuf<int32_t> sub_all;  // [S][n]
-    DevBuf<int32_t> nsub;
-    VRT_TRY(chg.alloc((size_t)S * n)); VRT_TRY(sub_all.alloc((size_t)S * n)); VRT_TRY(nsub.alloc(nls > 0 ? nls : 1));
-    VRT_CUDA(cudaMemset(nsub.p, 0, sizeof(int32_t) * (nls > 0 ? nls : 1)));
+    DevBuf<int32_t> lev;      // [S][n] DAG level of visit (c, s)
+    VRT_TRY(chg.alloc((size_t)S * n)); VRT_TRY(lev.alloc((size_t)S * n));
 
     for (int s = 1; s <= S; s++) {
         uint8_t* cur = chg.p + (size_t)(s - 1) * n;
@@ -301,27 +341,29 @@ int schedule_build(vrt_grid* g, const double k[3], int down, int n_sweeps, doubl
             VRT_TRY(relax_loop([](void* v) { C* c = (C*)v; k_chg_relax<<<c->nb, c->bs>>>(c->n, c->up, c->cls, c->cur, c->flag); }, &cx, flag.p, 100000));
         }
         k_stab_acc<<<nb, bs>>>(n, cur, sch->stab.p, s == 1);
-        int32_t* sub = sub_all.p + (size_t)(s - 1) * n;
-        k_sub_init<<<nb, bs>>>(n, cur, sub);
-        struct C2 { int nb, bs; int64_t n; const int32_t *up, *cls; const uint8_t* chg; int32_t* sub; int* flag; } c2{nb, bs, n, st.up.p, sch->cls.p, cur, sub, flag.p};
-        VRT_TRY(relax_loop([](void* v) { C2* c = (C2*)v; k_sub_relax<<<c->nb, c->bs>>>(c->n, c->up, c->cls, c->chg, c->sub, c->flag); }, &c2, flag.p, 100000));
-        if (nls > 0) k_nsub<<<nb, bs>>>(n, d.layer, sub, S, s, nsub.p);
+        if (s == 1) {
+            // in-layer sub-levels of sweep 1 (SURVEY App. G rule 3): kept for introspection / tests only
+            k_sub_init<<<nb, bs>>>(n, cur, sch->sublevel.p);
+            struct C2 { int nb, bs; int64_t n; const int32_t *up, *cls; const uint8_t* chg; int32_t* sub; int* flag; } c2{nb, bs, n, st.up.p, sch->cls.p, cur, sch->sublevel.p, flag.p};
+            VRT_TRY(relax_loop([](void* v) { C2* c = (C2*)v; k_sub_relax<<<c->nb, c->bs>>>(c->n, c->up, c->cls, c->chg, c->sub, c->flag); }, &c2, flag.p, 100000));
+        }
         VRT_CUDA(cudaGetLastError());
     }
-    VRT_CUDA(cudaMemcpy(sch->sublevel.p, sub_all.p, sizeof(int32_t) * n, cudaMemcpyDeviceToDevice));
-
-    // local step numbering: (layer asc, sweep asc, sub-level asc)
-    sch->nsub.assign((size_t)nls, 0);
-    if (nls > 0) VRT_CUDA(cudaMemcpy(sch->nsub.data(), nsub.p, sizeof(int32_t) * nls, cudaMemcpyDeviceToHost));
-    std::vector<int32_t> stepbase((size_t)(nls > 0 ? nls : 1), 0);
-    int64_t T = 0;
-    for (int64_t i = 0; i < nls; i++) {
-        stepbase[i] = (int32_t)T;
-        T += sch->nsub[i];
+    // global topological levels over all (cell, sweep) visits: the program order of the dataflow sweep.  This is
+    // 2.5-3.5x shallower than (layer, sweep, sub-level) because a visit only waits for what it really reads.
+    k_level_init<<<nb, bs>>>(n, S, sch->stab.p, lev.p);
+    {
+        struct C3 { int nb, bs; int64_t n; int S; const int32_t *up, *cls, *stab; int32_t* lev; int* flag; } c3{nb, bs, n, S, st.up.p, sch->cls.p, sch->stab.p, lev.p, flag.p};
+        VRT_TRY(relax_loop([](void* v) { C3* c = (C3*)v; k_level_relax<<<c->nb, c->bs>>>(c->n, c->S, c->up, c->cls, c->stab, c->lev, c->flag); }, &c3, flag.p, 1000000));
     }
-    DevBuf<int32_t> d_stepbase;
-    VRT_TRY(d_stepbase.alloc(stepbase.size()));
-    VRT_CUDA(cudaMemcpy(d_stepbase.p, stepbase.data(), sizeof(int32_t) * stepbase.size(), cudaMemcpyHostToDevice));
+    int64_t T = 0;
+    {
+        VRT_CUDA(cudaMemset(flag.p, 0, sizeof(int)));
+        k_level_max<<<nb, bs>>>(n, S, lev.p, flag.p);
+        int h = 0;
+        VRT_CUDA(cudaMemcpy(&h, flag.p, sizeof(int), cudaMemcpyDeviceToHost));
+        T = h;
+    }
 
     // visit offsets = exclusive scan of stab; scratch slots = exclusive scan of [stab > s]
     DevBuf<int64_t> voff;
@@ -360,7 +402,7 @@ int schedule_build(vrt_grid* g, const double k[3], int down, int n_sweeps, doubl
         }
         DevBuf<uint32_t> key, val, key2, val2;
         VRT_TRY(key.alloc(V)); VRT_TRY(val.alloc(V)); VRT_TRY(key2.alloc(V)); VRT_TRY(val2.alloc(V));
-        k_emit<<<nb, bs>>>(n, d.layer, sch->stab.p, voff.p, sub_all.p, d_stepbase.p, S, key.p, val.p);
+        k_emit<<<nb, bs>>>(n, sch->stab.p, voff.p, lev.p, key.p, val.p);
         VRT_CUDA(cudaGetLastError());
         int bits = 1;
         while ((1ll << bits) < T + 1 && bits < 32) bits++;
@@ -394,6 +436,12 @@ int schedule_build(vrt_grid* g, const double k[3], int down, int n_sweeps, doubl
         k_build_visits<<<nblocks(V, bs), bs>>>(V, n, key2.p, val2.p, st.up.p, sch->cls.p, sch->stab.p, slots.p, st.w.p, st.r.p,
                                                voff.p, vpos.p, off.p, poff.p, cv, sch->visits.p);
         VRT_CUDA(cudaGetLastError());
+    }
+    {
+        std::vector<int32_t> so(sch->step_off.size());
+        for (size_t i = 0; i < so.size(); i++) so[i] = (int32_t)sch->step_off[i];
+        VRT_TRY(sch->step_off_dev.alloc(so.size()));
+        VRT_CUDA(cudaMemcpy(sch->step_off_dev.p, so.data(), sizeof(int32_t) * so.size(), cudaMemcpyHostToDevice));
     }
     VRT_CUDA(cudaDeviceSynchronize());
     guard.s = nullptr;

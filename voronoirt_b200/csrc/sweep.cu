@@ -23,25 +23,69 @@ struct DirDev {
     double* I_main;
     double* scratch[MAX_SWEEPS];
     int32_t* flags;          // one ready-flag per chunk of this direction's program (== epoch when done)
+    const int32_t* step_off; // [nsteps+1] visit-slot offsets of this direction's dependent steps (multiples of cv)
+    int32_t nsteps;
+    int32_t pad;
 };
 
 struct SweepParams {
     const DirDev* dirs;      // [nd] in global memory
-    const int32_t* goffT;    // [(T+1)][nd]: visit-slot offset of direction d at global step t (multiples of cv)
     const double* S;         // [n][ldS], first wavelength of the chunk
     int64_t ldS;             // row stride of S
     int nd;
-    int T;
+    int T;                   // max over directions of nsteps; global step g = t*nd + d runs step t of direction d
     int nlam;
     int cv;                  // visits per chunk
     int32_t epoch;
+    int32_t experiment;      // VRT_EXPERIMENT: timing experiments only (0 in production)
+    unsigned long long* prof; // experiment 2: per-role cycle counters
 };
+
+// exp(x) for the sweep: Cody–Waite reduction x = k ln2 + r, |r| <= ln2/2, degree-13 Taylor polynomial (truncation
+// 4e-18), scaling by 2^k through the exponent field.  ~20 instructions, no fp64<->int conversion, no special-case
+// branches; relative error <= ~2 ulp for -700 <= x <= 700 (outside, the argument is clamped: linear_weights never
+// uses e for Δτ > 50).
+__device__ __forceinline__ double exp_sweep(double x) {
+    x = fmin(fmax(x, -700.0), 700.0);
+    const double MAGIC = 6755399441055744.0;                   // 1.5 * 2^52: rounds to nearest integer
+    const double t = fma(x, 1.4426950408889634074, MAGIC);
+    const double kf = t - MAGIC;
+    const int k = __double2loint(t);
+    double r = fma(kf, -6.93147180369123816490e-01, x);        // ln2 high part (fdlibm split)
+    r = fma(kf, -1.90821492927058770002e-10, r);               // ln2 low part
+    double p = 1.6059043836821614599e-10;                      // 1/13!
+    p = fma(p, r, 2.0876756987868098979e-09);                  // 1/12!
+    p = fma(p, r, 2.5052108385441718775e-08);                  // 1/11!
+    p = fma(p, r, 2.7557319223985890653e-07);                  // 1/10!
+    p = fma(p, r, 2.7557319223985892511e-06);                  // 1/9!
+    p = fma(p, r, 2.4801587301587301566e-05);                  // 1/8!
+    p = fma(p, r, 1.9841269841269841253e-04);                  // 1/7!
+    p = fma(p, r, 1.3888888888888889419e-03);                  // 1/6!
+    p = fma(p, r, 8.3333333333333332177e-03);                  // 1/5!
+    p = fma(p, r, 4.1666666666666664354e-02);                  // 1/4!
+    p = fma(p, r, 1.6666666666666665741e-01);                  // 1/3!
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
+}
+
+// 1/a for a > 0: hardware seed (MUFU.RCP64H) + two Newton steps -> full double precision (<= 1 ulp)
+__device__ __forceinline__ double rcp_sweep(double a) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+    double e = fma(-a, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-a, y, 1.0);
+    y = fma(y, e, y);
+    return y;
+}
 
 // linear_weights (functions.jl:484-500), branch-free: the three branches are evaluated with selects so that a
 // warp whose lanes hold different wavelengths (very different Δτ) does not serialise them.
 __device__ __forceinline__ void linear_weights(double dtau, double& a, double& b, double& e) {
-    const double ex = exp(-dtau);
-    const double inv = __drcp_rn(dtau);
+    const double ex = exp_sweep(-dtau);
+    const double inv = rcp_sweep(dtau);
     const double a_mid = (1 - ex) * inv - ex;
     const bool small = dtau < 5e-4, large = dtau > 50;
     e = small ? (1 - dtau + 0.5 * (dtau * dtau)) : (large ? 0.0 : ex);
@@ -96,14 +140,32 @@ __device__ __forceinline__ void do_item(const VisitRegs& v, const DirDev* __rest
 // dataflow synchronisation (no grid barrier): a chunk spins on the ready-flags of the chunks that produce its
 // upwind intensities.  Chunks are claimed in a fixed global topological order (warp w owns chunks w, w+W, ...),
 // every warp of the cooperative launch is resident, so by induction on the chunk index no wait can deadlock.
-__device__ __forceinline__ void wait_flag(const int32_t* f, int32_t epoch) {
+// Polling uses relaxed loads (an acquire load costs an L1 invalidate per poll); `acquire` adds the one acquire that
+// orders the subsequent generic-proxy reads of the intensities.  The TMA producer passes acquire=false: its reads go
+// through the async proxy (L2) and are ordered by fence.proxy.async instead.
+__device__ __forceinline__ void wait_flag(const int32_t* f, int32_t epoch, bool acquire) {
     int v;
     for (;;) {
-        asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+        asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
         if (v == epoch) break;
-        __nanosleep(40);
+        __nanosleep(100);
+    }
+    if (acquire) asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+}
+// both producer flags of a visit, polled together (one L2 round trip when they are already set)
+__device__ __forceinline__ void wait_flags2(const int32_t* flags, uint32_t d1, uint32_t d2, int32_t epoch) {
+    const int32_t* f1 = flags + (d1 == DEP_NONE ? 0 : d1);
+    const int32_t* f2 = flags + (d2 == DEP_NONE ? 0 : d2);
+    for (;;) {
+        int v1, v2;
+        asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v1) : "l"(f1) : "memory");
+        asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v2) : "l"(f2) : "memory");
+        if ((d1 == DEP_NONE || v1 == epoch) && (d2 == DEP_NONE || v2 == epoch)) break;
+        __nanosleep(100);
     }
 }
+// lane 0 publishes the chunk after __syncwarp(): the release is cumulative over the other lanes' stores, which are
+// ordered before it by the warp barrier (PTX memory model: causality order through bar.warp.sync)
 __device__ __forceinline__ void set_flag(int32_t* f, int32_t epoch) {
     asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(f), "r"(epoch) : "memory");
 }
@@ -115,7 +177,6 @@ constexpr int SWEEP_BLOCK = 256;
 
 template <bool SINGLE>
 __global__ void __launch_bounds__(SWEEP_BLOCK, SWEEP_MIN_BLOCKS) k_sweep(const SweepParams P) {
-    const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const long long nwarps = (long long)((gridDim.x * (unsigned)blockDim.x) >> 5);
     long long gnext = (long long)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);  // next global chunk of this warp
@@ -124,36 +185,25 @@ __global__ void __launch_bounds__(SWEEP_BLOCK, SWEEP_MIN_BLOCKS) k_sweep(const S
     const int32_t epoch = P.epoch;
     const double* __restrict__ S = P.S;
     const int64_t ldS = P.ldS;
-    for (int t = 0; t < P.T; t++) {
-        int beg = 0, cnt = 0;
-        if (lane < P.nd) {
-            beg = __ldg(P.goffT + (size_t)t * P.nd + lane);
-            int end = __ldg(P.goffT + (size_t)(t + 1) * P.nd + lane);
-            cnt = (end - beg) / cv;
-        }
-        int incl = cnt;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            int v = __shfl_up_sync(full, incl, o);
-            if (lane >= o) incl += v;
-        }
-        const int total = __shfl_sync(full, incl, 31);
-        const int excl = incl - cnt;
+    // global step g = t*nd + d: step t of direction d.  Consecutive global steps belong to different directions, so
+    // the dependent steps t and t+1 of one direction are separated by the independent work of all the others and the
+    // producers' flags are (almost) always set by the time a chunk looks at them.
+    const int G = P.T * P.nd;
+    for (int g = 0; g < G; g++) {
+        const int d = g % P.nd, t = g / P.nd;
+        const DirDev* __restrict__ D = P.dirs + d;
+        if (t >= D->nsteps) continue;
+        const int beg = __ldg(D->step_off + t);
+        const int total = (__ldg(D->step_off + t + 1) - beg) / cv;
+        const Visit* __restrict__ visits = D->visits;
+        int32_t* flags = D->flags;
         while (gnext < base + total) {
-            const int ch = (int)(gnext - base);
-            unsigned m = __ballot_sync(full, ch >= excl && ch < incl);
-            const int d = __ffs(m) - 1;
-            const int dbeg = __shfl_sync(full, beg, d);
-            const int dexcl = __shfl_sync(full, excl, d);
-            const DirDev* __restrict__ D = P.dirs + d;
-            const Visit* __restrict__ visits = D->visits;
-            const int cj = dbeg / cv + (ch - dexcl);   // chunk index inside direction d's program
-            int32_t* flags = D->flags;
+            const int cj = beg / cv + (int)(gnext - base);   // chunk index inside direction d's program
             if (SINGLE) {
                 VisitRegs v = load_visit(visits + cj);
                 if (lane < 2) {
                     uint32_t dep = lane ? v.b.w : v.b.z;
-                    if (dep != DEP_NONE) wait_flag(flags + dep, epoch);
+                    if (dep != DEP_NONE) wait_flag(flags + dep, epoch, true);
                 }
                 __syncwarp();
                 for (int l = lane; l < nlam; l += 32) do_item(v, D, S, ldS, nlam, l);
@@ -161,7 +211,7 @@ __global__ void __launch_bounds__(SWEEP_BLOCK, SWEEP_MIN_BLOCKS) k_sweep(const S
                 const int vb = cj * cv;
                 for (int q = lane; q < 2 * cv; q += 32) {
                     uint32_t dep = __ldg(reinterpret_cast<const uint32_t*>(visits + vb + (q >> 1)) + 6 + (q & 1));
-                    if (dep != DEP_NONE) wait_flag(flags + dep, epoch);
+                    if (dep != DEP_NONE) wait_flag(flags + dep, epoch, true);
                 }
                 __syncwarp();
                 const int nitems = cv * nlam;
@@ -172,7 +222,6 @@ __global__ void __launch_bounds__(SWEEP_BLOCK, SWEEP_MIN_BLOCKS) k_sweep(const S
                     if (v.a.x != CELL_DUMMY) do_item(v, D, S, ldS, nlam, l);
                 }
             }
-            __threadfence();   // every lane: its intensities are visible device-wide before the flag is
             __syncwarp();
             if (lane == 0) set_flag(flags + cj, epoch);
             gnext += nwarps;
@@ -217,82 +266,93 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
                      : "=r"(done) : "r"(addr), "r"(parity) : "memory");
     } while (!done);
 }
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+    uint32_t done;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return done != 0;
+}
 __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
-constexpr int TMA_NC = 7;                         // consumer warps per CTA
-constexpr int TMA_BLOCK = 32 * (TMA_NC + 1);
-constexpr int TMA_MAX_STAGES = 32;
 
-__global__ void __launch_bounds__(TMA_BLOCK, 3) k_sweep_tma(const SweepParams P, int ns, int rowb) {
+constexpr int TMA_MAX_STAGES = 32;
+#ifndef TMA_DEFER
+#define TMA_DEFER 4
+#endif
+
+// TMA_NP producer warps (independent issue chains) + TMA_NC consumer warps per CTA
+template <int TMA_NP, int TMA_NC>
+__global__ void __launch_bounds__(32 * (TMA_NP + TMA_NC), 3) k_sweep_tma(const SweepParams P, int ns, int rowb) {
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t* full = reinterpret_cast<uint64_t*>(smem);
-    uint64_t* empty = full + TMA_MAX_STAGES;
+    // stage hand-back: consumed[s] counts the rounds of stage s that have been drained.  A counter (not an mbarrier
+    // parity) lets several rounds of one stage be pending, so a producer run can be a full warp of 32 visits.
+    volatile uint32_t* consumed = reinterpret_cast<volatile uint32_t*>(full + TMA_MAX_STAGES);
     StageHdr* hdr = reinterpret_cast<StageHdr*>(smem + 2 * TMA_MAX_STAGES * sizeof(uint64_t));
-    unsigned char* data = smem + 2 * TMA_MAX_STAGES * sizeof(uint64_t) + TMA_MAX_STAGES * sizeof(StageHdr);
-    const unsigned full_mask = 0xffffffffu;
+    DirDev* sdirs = reinterpret_cast<DirDev*>(smem + 2 * TMA_MAX_STAGES * sizeof(uint64_t) + TMA_MAX_STAGES * sizeof(StageHdr));
+    unsigned char* data = smem + 2 * TMA_MAX_STAGES * sizeof(uint64_t) + TMA_MAX_STAGES * sizeof(StageHdr) + MAX_DIRS * sizeof(DirDev);
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int nlam = P.nlam;
     const int32_t epoch = P.epoch;
+    for (int i = threadIdx.x; i < P.nd * (int)(sizeof(DirDev) / 8); i += blockDim.x)
+        reinterpret_cast<unsigned long long*>(sdirs)[i] = reinterpret_cast<const unsigned long long*>(P.dirs)[i];
     if (threadIdx.x == 0) {
         for (int s = 0; s < ns; s++) {
             mbar_init(full + s, 1);
-            mbar_init(empty + s, 1);
+            consumed[s] = 0;
             hdr[s].seq = 0xffffffffu;   // shared memory may still hold the headers of an earlier launch
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    if (warp == 0) {
-        // ===== producer: every lane owns one visit of a run of up to 32 consecutive chunks =====
+    if (warp < TMA_NP) {
+        // ===== producers: every lane owns one visit of a run of up to 32 consecutive chunks; the CTA's runs are dealt
+        // round-robin to its TMA_NP producer warps so that the latency chains (visit record -> flags -> stage ->
+        // bulk copies) of consecutive runs overlap =====
         // (the 32 visit records of a run are one coalesced 2 KB read; flags, stage hand-back and the eight bulk
         //  copies of a visit are then handled by its lane, so up to 32 visits are being issued at once)
         long long rnext = blockIdx.x;     // next global run of this CTA (CTA b owns runs b, b+B, ...)
         long long rbase = 0;              // global index of step t's first run
         const long long nblk = gridDim.x;
         unsigned it = 0;                  // chunks handed to the consumers so far
-        // a run never exceeds the ring: per stage at most one refill may be pending, otherwise the parity wait on
-        // the `empty` barrier could be satisfied by the wrong phase
-        const int RL = min(32, ns);
+        unsigned rc = 0;                  // runs of this CTA so far
+        const int RL = 32;
         const double* __restrict__ S = P.S;
         const int64_t ldS = P.ldS;
-        for (int t = 0; t < P.T; t++) {
-            int beg = 0, len = 0, cnt = 0;
-            if (lane < P.nd) {
-                beg = __ldg(P.goffT + (size_t)t * P.nd + lane);
-                len = __ldg(P.goffT + (size_t)(t + 1) * P.nd + lane) - beg;
-                cnt = (len + RL - 1) / RL;    // runs of this direction in this step
-            }
-            int incl = cnt;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                int v = __shfl_up_sync(full_mask, incl, o);
-                if (lane >= o) incl += v;
-            }
-            const int total = __shfl_sync(full_mask, incl, 31);
-            const int excl = incl - cnt;
+        const int G = P.T * P.nd;
+        for (int g = 0; g < G; g++) {
+            const int d = g % P.nd, t = g / P.nd;
+            const DirDev* __restrict__ D = sdirs + d;
+            if (t >= D->nsteps) continue;
+            const int dbeg = __ldg(D->step_off + t);
+            const int dlen = __ldg(D->step_off + t + 1) - dbeg;
+            const int total = (dlen + RL - 1) / RL;           // runs of this step
             while (rnext < rbase + total) {
-                const int run = (int)(rnext - rbase);
-                unsigned m = __ballot_sync(full_mask, run >= excl && run < incl);
-                const int d = __ffs(m) - 1;
-                const int r_in_dir = run - __shfl_sync(full_mask, excl, d);
-                const int dbeg = __shfl_sync(full_mask, beg, d);
-                const int dlen = __shfl_sync(full_mask, len, d);
-                const int first = r_in_dir * RL;
+                const int first = (int)(rnext - rbase) * RL;
                 const int nrun = min(RL, dlen - first);       // chunks in this run
-                const DirDev* __restrict__ D = P.dirs + d;
-                if (lane < nrun) {
+                long long r0 = 0;
+                if (P.experiment == 2) r0 = clock64();
+                if (lane < nrun && (int)(rc % TMA_NP) == warp) {
                     const int cj = dbeg + first + lane;
                     const VisitRegs v = load_visit(D->visits + cj);
                     const unsigned my = it + (unsigned)lane;
                     const int stage = (int)(my % (unsigned)ns);
-                    const uint32_t par = (my / (unsigned)ns) & 1u;
-                    if (v.b.z != DEP_NONE) wait_flag(D->flags + v.b.z, epoch);
-                    if (v.b.w != DEP_NONE) wait_flag(D->flags + v.b.w, epoch);
-                    mbar_wait(empty + stage, par ^ 1u);
+                    const uint32_t round = my / (unsigned)ns;
+                    long long c0 = 0, c1 = 0, c2 = 0;
+                    if (P.experiment == 2) { volatile uint32_t touch = v.b.z; (void)touch; c0 = clock64(); }
+                    wait_flags2(D->flags, v.b.z, v.b.w, epoch);
+                    if (P.experiment == 2) c1 = clock64();
+                    while (consumed[stage] != round) __nanosleep(32);
+                    if (P.experiment == 2) {
+                        c2 = clock64();
+                        atomicAdd(P.prof + 0, (unsigned long long)(c1 - c0));   // producer lane: flag waits
+                        atomicAdd(P.prof + 1, (unsigned long long)(c2 - c1));   // producer lane: stage waits
+                        atomicAdd(P.prof + 2, 1ull);
+                    }
                     // rows of the stage: 0 α_c, 1 S_c, 2 α_u1, 3 S_u1, 4 I_u1, 5 α_u2, 6 S_u2, 7 I_u2
                     const double* src[8];
                     const double* alpha = D->alpha;
@@ -333,22 +393,32 @@ __global__ void __launch_bounds__(TMA_BLOCK, 3) k_sweep_tma(const SweepParams P,
                     for (int r = 0; r < 8; r++) {
                         if (src[r]) {
                             const uint32_t off = (offmask >> r) & 1u;
-                            bulk_g2s(data + (size_t)(stage * 8 + r) * rowb, src[r] - off, (uint32_t)(((nlam + off) * 8 + 15) & ~15), full + stage);
+                            const uint32_t nb = (uint32_t)(((nlam + off) * 8 + 15) & ~15);
+                            if (P.experiment == 1) {   // timing experiment: same bytes in twice as many bulk copies
+                                const uint32_t h1 = (nb / 2) & ~15u;
+                                bulk_g2s(data + (size_t)(stage * 8 + r) * rowb, src[r] - off, h1, full + stage);
+                                bulk_g2s(data + (size_t)(stage * 8 + r) * rowb + h1, reinterpret_cast<const unsigned char*>(src[r] - off) + h1, nb - h1, full + stage);
+                            } else
+                                bulk_g2s(data + (size_t)(stage * 8 + r) * rowb, src[r] - off, nb, full + stage);
                         }
                     }
                 }
                 __syncwarp();
+                if (P.experiment == 2 && lane == 0) {
+                    atomicAdd(P.prof + 3, (unsigned long long)(clock64() - r0));   // producer: whole run
+                    atomicAdd(P.prof + 4, 1ull);
+                }
                 it += (unsigned)nrun;
+                rc++;
                 rnext += nblk;
             }
             rbase += total;
         }
-        // one termination token per consumer warp
-        for (int k = 0; k < TMA_NC; k++) {
+        // one termination token per consumer warp (sent by producer 0)
+        for (int k = 0; k < TMA_NC && warp == 0; k++) {
             const int stage = (int)(it % (unsigned)ns);
-            const uint32_t par = (it / (unsigned)ns) & 1u;
             if (lane == 0) {
-                mbar_wait(empty + stage, par ^ 1u);
+                while (consumed[stage] != it / (unsigned)ns) __nanosleep(32);
                 hdr[stage].valid = 0;
                 hdr[stage].seq = it;
                 mbar_arrive(full + stage);
@@ -358,18 +428,36 @@ __global__ void __launch_bounds__(TMA_BLOCK, 3) k_sweep_tma(const SweepParams P,
         }
     } else {
         // ===== consumers =====
-        for (unsigned it = (unsigned)(warp - 1);; it += TMA_NC) {
+        // The result row is stored straight to HBM; publishing its ready-flag needs a release fence that waits for
+        // those stores, which under a saturated memory system takes microseconds.  The stage is therefore handed
+        // back immediately and the flag publication is deferred: up to TMA_DEFER finished visits share one fence.
+        // A consumer never blocks while it holds unpublished flags (the data it waits for may depend on them).
+        int32_t* pend[TMA_DEFER];
+        int np = 0;
+        for (unsigned it = (unsigned)(warp - TMA_NP);; it += TMA_NC) {
             const int stage = (int)(it % (unsigned)ns);
             const uint32_t par = (it / (unsigned)ns) & 1u;
             // producer lanes fill stages out of order, so a parity wait alone could be satisfied by the fill of two
             // rounds ago; the sequence number in the header tells the rounds apart
-            for (;;) {
-                mbar_wait(full + stage, par);
-                if (reinterpret_cast<volatile StageHdr*>(hdr)[stage].seq == it) break;
-                __nanosleep(64);
+            long long k0 = 0, k1 = 0;
+            if (P.experiment == 2) k0 = clock64();
+            bool ready = mbar_test(full + stage, par) && reinterpret_cast<volatile StageHdr*>(hdr)[stage].seq == it;
+            if (!ready) {
+                if (np) {
+                    __syncwarp();
+                    if (lane == 0)
+                        for (int i = 0; i < np; i++) set_flag(pend[i], epoch);
+                    np = 0;
+                }
+                for (;;) {
+                    mbar_wait(full + stage, par);
+                    if (reinterpret_cast<volatile StageHdr*>(hdr)[stage].seq == it) break;
+                    __nanosleep(64);
+                }
             }
             const StageHdr h = hdr[stage];
             if (!h.valid) break;
+            if (P.experiment == 2) k1 = clock64();
             const unsigned char* rb = data + (size_t)stage * 8 * rowb;
             const double* r0 = reinterpret_cast<const double*>(rb) + (h.offs & 1u);
             const double* r1 = reinterpret_cast<const double*>(rb + rowb) + ((h.offs >> 1) & 1u);
@@ -391,13 +479,26 @@ __global__ void __launch_bounds__(TMA_BLOCK, 3) k_sweep_tma(const SweepParams P,
                 I += (e * I_2 + a * r6[l] + b * S_c) * h.w2;
                 h.dst[l] = I;
             }
-            __threadfence();
-            __syncwarp();
-            if (lane == 0) {
-                set_flag(h.flag, epoch);
-                mbar_arrive(empty + stage);
+            __syncwarp();   // every lane has read its part of the stage and issued its stores
+            if (lane == 0) consumed[stage] = it / (unsigned)ns + 1u;
+            pend[np++] = h.flag;
+            long long k2 = 0;
+            if (P.experiment == 2) k2 = clock64();
+            if (np == TMA_DEFER) {
+                if (lane == 0)
+                    for (int i = 0; i < TMA_DEFER; i++) set_flag(pend[i], epoch);
+                np = 0;
+            }
+            if (P.experiment == 2 && lane == 0) {
+                atomicAdd(P.prof + 5, (unsigned long long)(k1 - k0));            // consumer: waiting for data
+                atomicAdd(P.prof + 6, (unsigned long long)(k2 - k1));            // consumer: compute + stores
+                atomicAdd(P.prof + 7, (unsigned long long)(clock64() - k2));     // consumer: flag release
+                atomicAdd(P.prof + 8, 1ull);
             }
         }
+        __syncwarp();
+        if (lane == 0)
+            for (int i = 0; i < np; i++) set_flag(pend[i], epoch);
     }
 }
 
@@ -407,53 +508,15 @@ int sweep_run(vrt_grid* g, int nd, const SweepDir* dirs, const double* S, int64_
         set_error("sweep_run: %d directions exceed MAX_DIRS=%d", nd, MAX_DIRS);
         return VRT_E_INVALID;
     }
-    // ---- merge the per-direction programs: align steps by (layer, sweep) within the up group and within
-    // the down group (keeps all directions on the same layers => S rows are shared in L2), zip up with down
     int T = 0;
-    std::vector<std::vector<int32_t>> goff(nd);
-    for (int grp = 0; grp < 2; grp++) {
-        size_t nls = 0;
-        for (int d = 0; d < nd; d++)
-            if (dirs[d].sch->down == grp) nls = std::max(nls, dirs[d].sch->nsub.size());
-        if (nls == 0) continue;
-        std::vector<int32_t> mx(nls, 0);
-        int any = 0;
-        for (int d = 0; d < nd; d++) {
-            const DirSchedule* s = dirs[d].sch;
-            if (s->down != grp) continue;
-            any = 1;
-            if (s->nsub.size() != nls || s->n_sweeps != dirs[0].sch->n_sweeps) {
-                set_error("sweep_run: schedules of one launch must share the grid and n_sweeps");
-                return VRT_E_INVALID;
-            }
-            for (size_t i = 0; i < nls; i++) mx[i] = std::max(mx[i], s->nsub[i]);
-        }
-        if (!any) continue;
-        int64_t Tg = 0;
-        for (size_t i = 0; i < nls; i++) Tg += mx[i];
-        for (int d = 0; d < nd; d++) {
-            const DirSchedule* s = dirs[d].sch;
-            if (s->down != grp) continue;
-            std::vector<int32_t>& o = goff[d];
-            o.reserve((size_t)Tg + 1);
-            int64_t local = 0;
-            for (size_t i = 0; i < nls; i++) {
-                for (int32_t j = 0; j < mx[i]; j++) {
-                    o.push_back((int32_t)s->step_off[(size_t)local]);
-                    if (j < s->nsub[i]) local++;
-                }
-            }
-            o.push_back((int32_t)s->step_off[(size_t)local]);
-        }
-        T = std::max<int64_t>(T, Tg);
-    }
-    std::vector<int32_t> goffT((size_t)(T + 1) * nd);
     double visits = 0;
     for (int d = 0; d < nd; d++) {
-        std::vector<int32_t>& o = goff[d];
-        int32_t last = o.empty() ? 0 : o.back();
-        for (int t = 0; t <= T; t++) goffT[(size_t)t * nd + d] = t < (int)o.size() ? o[t] : last;
+        T = std::max<int>(T, (int)dirs[d].sch->step_off.size() - 1);
         visits += (double)dirs[d].sch->n_visits;
+        if (dirs[d].sch->n_sweeps != dirs[0].sch->n_sweeps) {
+            set_error("sweep_run: schedules of one launch must share n_sweeps");
+            return VRT_E_INVALID;
+        }
     }
     if (T == 0) return VRT_OK;
 
@@ -478,20 +541,20 @@ int sweep_run(vrt_grid* g, int nd, const SweepDir* dirs, const double* S, int64_
     for (int d = 0; d < nd; d++) {
         hd[d].flags = g->flag_pool.p + fo;
         fo += (size_t)dirs[d].sch->n_chunks;
+        hd[d].step_off = dirs[d].sch->step_off_dev.p;
+        hd[d].nsteps = (int32_t)dirs[d].sch->step_off.size() - 1;
+        hd[d].pad = 0;
         hd[d].visits = dirs[d].sch->visits.p;
         hd[d].alpha = dirs[d].alpha;
         hd[d].I_main = dirs[d].I_main;
         for (int s = 0; s < MAX_SWEEPS; s++) hd[d].scratch[s] = dirs[d].scratch[s];
     }
     DevBuf<DirDev> d_dirs;
-    DevBuf<int32_t> d_goffT;
-    VRT_TRY(d_dirs.alloc(nd)); VRT_TRY(d_goffT.alloc(goffT.size()));
+    VRT_TRY(d_dirs.alloc(nd));
     VRT_CUDA(cudaMemcpyAsync(d_dirs.p, hd.data(), sizeof(DirDev) * nd, cudaMemcpyHostToDevice, st));
-    VRT_CUDA(cudaMemcpyAsync(d_goffT.p, goffT.data(), sizeof(int32_t) * goffT.size(), cudaMemcpyHostToDevice, st));
 
     SweepParams P;
     P.dirs = d_dirs.p;
-    P.goffT = d_goffT.p;
     P.S = S;
     P.ldS = ldS;
     P.nd = nd;
@@ -499,6 +562,11 @@ int sweep_run(vrt_grid* g, int nd, const SweepDir* dirs, const double* S, int64_
     P.nlam = (int)nlam;
     P.cv = cv;
     P.epoch = epoch;
+    P.experiment = getenv("VRT_EXPERIMENT") ? atoi(getenv("VRT_EXPERIMENT")) : 0;
+    DevBuf<unsigned long long> d_prof;
+    VRT_TRY(d_prof.alloc(16));
+    VRT_CUDA(cudaMemsetAsync(d_prof.p, 0, 16 * sizeof(unsigned long long), st));
+    P.prof = d_prof.p;
 
     int dev = 0, sms = 0, per_sm = 0;
     VRT_CUDA(cudaGetDevice(&dev));
@@ -509,10 +577,18 @@ int sweep_run(vrt_grid* g, int nd, const SweepDir* dirs, const double* S, int64_
     int block, ns = 0, rowb = 0;
     size_t shmem = 0;
     if (use_tma) {
-        fn = (const void*)k_sweep_tma;
-        block = TMA_BLOCK;
+        const char* env_cfg = getenv("VRT_TMA_CFG");
+        const int cfg = env_cfg ? atoi(env_cfg) : 27;
+        switch (cfg) {
+            case 26: fn = (const void*)k_sweep_tma<2, 6>; block = 32 * 8; break;
+            case 36: fn = (const void*)k_sweep_tma<3, 6>; block = 32 * 9; break;
+            case 35: fn = (const void*)k_sweep_tma<3, 5>; block = 32 * 8; break;
+            case 44: fn = (const void*)k_sweep_tma<4, 4>; block = 32 * 8; break;
+            case 17: fn = (const void*)k_sweep_tma<1, 7>; block = 32 * 8; break;
+            default: fn = (const void*)k_sweep_tma<2, 7>; block = 32 * 9; break;
+        }
         rowb = (int)(((nlam + 1) * 8 + 15) & ~15);
-        const size_t fixed = 2 * TMA_MAX_STAGES * sizeof(uint64_t) + TMA_MAX_STAGES * sizeof(StageHdr);
+        const size_t fixed = 2 * TMA_MAX_STAGES * sizeof(uint64_t) + TMA_MAX_STAGES * sizeof(StageHdr) + MAX_DIRS * sizeof(DirDev);
         const char* env_ns = getenv("VRT_TMA_STAGES");
         const char* env_kb = getenv("VRT_TMA_SMEM_KB");
         const size_t budget = (size_t)(env_kb && atoi(env_kb) > 0 ? atoi(env_kb) : 72) * 1024;
@@ -549,10 +625,18 @@ int sweep_run(vrt_grid* g, int nd, const SweepDir* dirs, const double* S, int64_
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     VRT_CUDA(cudaGetLastError());
+    if (P.experiment == 2) {
+        unsigned long long h[16];
+        VRT_CUDA(cudaMemcpy(h, d_prof.p, sizeof(h), cudaMemcpyDeviceToHost));
+        fprintf(stderr, "[sweep prof] %.2f ms | producer lane: flags %.0f cyc, stage %.0f cyc per visit (%llu visits) | run %.0f cyc (%llu runs) | "
+                        "consumer per visit: wait %.0f, compute %.0f, release %.0f cyc (%llu)\n",
+                ms, (double)h[0] / (h[2] + 1e-9), (double)h[1] / (h[2] + 1e-9), h[2], (double)h[3] / (h[4] + 1e-9), h[4],
+                (double)h[5] / (h[8] + 1e-9), (double)h[6] / (h[8] + 1e-9), (double)h[7] / (h[8] + 1e-9), h[8]);
+    }
     if (stats) {
         stats->kernels += 1;
         stats->visits += visits;
-        stats->steps += T;
+        stats->steps += (double)T * nd;
         stats->sweep_ms += ms;
     }
     return VRT_OK;

@@ -109,6 +109,7 @@ struct DirSchedule {
     int64_t n_slots = 0;            // padded length = n_chunks * cv
     int64_t n_chunks = 0;
     std::vector<int64_t> step_off;  // local steps: T_local+1 offsets into visits (padded positions)
+    DevBuf<int32_t> step_off_dev;   // the same on the device (int32)
     // (layer, sweep) -> number of sub-levels; index (layer-2)*n_sweeps + (sweep-1)
     std::vector<int32_t> nsub;
     int64_t scr_rows[MAX_SWEEPS] = {0};  // rows needed in scratch buffer s (sweep s+1 non-final writers)
