@@ -169,6 +169,12 @@ __device__ __forceinline__ void wait_flags2(const int32_t* flags, uint32_t d1, u
 __device__ __forceinline__ void set_flag(int32_t* f, int32_t epoch) {
     asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(f), "r"(epoch) : "memory");
 }
+// several chunks at once: ONE release fence (it waits for the outstanding result stores), then relaxed flag stores.
+// Back-to-back st.release would each wait a full store round trip.
+__device__ __forceinline__ void set_flags(int32_t* const* f, int n, int32_t epoch) {
+    asm volatile("fence.acq_rel.gpu;" ::: "memory");
+    for (int i = 0; i < n; i++) asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(f[i]), "r"(epoch) : "memory");
+}
 
 constexpr int SWEEP_BLOCK = 256;
 #ifndef SWEEP_MIN_BLOCKS
@@ -280,7 +286,7 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint3
 
 constexpr int TMA_MAX_STAGES = 32;
 #ifndef TMA_DEFER
-#define TMA_DEFER 4
+#define TMA_DEFER 6
 #endif
 
 // TMA_NP producer warps (independent issue chains) + TMA_NC consumer warps per CTA
@@ -291,6 +297,7 @@ __global__ void __launch_bounds__(32 * (TMA_NP + TMA_NC), 3) k_sweep_tma(const S
     // stage hand-back: consumed[s] counts the rounds of stage s that have been drained.  A counter (not an mbarrier
     // parity) lets several rounds of one stage be pending, so a producer run can be a full warp of 32 visits.
     volatile uint32_t* consumed = reinterpret_cast<volatile uint32_t*>(full + TMA_MAX_STAGES);
+    unsigned int* next_chunk = const_cast<unsigned int*>(reinterpret_cast<volatile unsigned int*>(consumed + TMA_MAX_STAGES));   // consumer dispatch counter
     StageHdr* hdr = reinterpret_cast<StageHdr*>(smem + 2 * TMA_MAX_STAGES * sizeof(uint64_t));
     DirDev* sdirs = reinterpret_cast<DirDev*>(smem + 2 * TMA_MAX_STAGES * sizeof(uint64_t) + TMA_MAX_STAGES * sizeof(StageHdr));
     unsigned char* data = smem + 2 * TMA_MAX_STAGES * sizeof(uint64_t) + TMA_MAX_STAGES * sizeof(StageHdr) + MAX_DIRS * sizeof(DirDev);
@@ -304,6 +311,7 @@ __global__ void __launch_bounds__(32 * (TMA_NP + TMA_NC), 3) k_sweep_tma(const S
         for (int s = 0; s < ns; s++) {
             mbar_init(full + s, 1);
             consumed[s] = 0;
+            if (s == 0) *next_chunk = 0;
             hdr[s].seq = 0xffffffffu;   // shared memory may still hold the headers of an earlier launch
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -434,7 +442,11 @@ __global__ void __launch_bounds__(32 * (TMA_NP + TMA_NC), 3) k_sweep_tma(const S
         // A consumer never blocks while it holds unpublished flags (the data it waits for may depend on them).
         int32_t* pend[TMA_DEFER];
         int np = 0;
-        for (unsigned it = (unsigned)(warp - TMA_NP);; it += TMA_NC) {
+        // chunks are dispatched dynamically: whichever consumer warp is free takes the next chunk of the CTA's sequence
+        for (;;) {
+            unsigned it = 0;
+            if (lane == 0) it = atomicAdd(next_chunk, 1u);
+            it = __shfl_sync(0xffffffffu, it, 0);
             const int stage = (int)(it % (unsigned)ns);
             const uint32_t par = (it / (unsigned)ns) & 1u;
             // producer lanes fill stages out of order, so a parity wait alone could be satisfied by the fill of two
@@ -445,8 +457,7 @@ __global__ void __launch_bounds__(32 * (TMA_NP + TMA_NC), 3) k_sweep_tma(const S
             if (!ready) {
                 if (np) {
                     __syncwarp();
-                    if (lane == 0)
-                        for (int i = 0; i < np; i++) set_flag(pend[i], epoch);
+                    if (lane == 0) set_flags(pend, np, epoch);
                     np = 0;
                 }
                 for (;;) {
@@ -485,8 +496,7 @@ __global__ void __launch_bounds__(32 * (TMA_NP + TMA_NC), 3) k_sweep_tma(const S
             long long k2 = 0;
             if (P.experiment == 2) k2 = clock64();
             if (np == TMA_DEFER) {
-                if (lane == 0)
-                    for (int i = 0; i < TMA_DEFER; i++) set_flag(pend[i], epoch);
+                if (lane == 0) set_flags(pend, TMA_DEFER, epoch);
                 np = 0;
             }
             if (P.experiment == 2 && lane == 0) {
@@ -497,8 +507,7 @@ __global__ void __launch_bounds__(32 * (TMA_NP + TMA_NC), 3) k_sweep_tma(const S
             }
         }
         __syncwarp();
-        if (lane == 0)
-            for (int i = 0; i < np; i++) set_flag(pend[i], epoch);
+        if (lane == 0) set_flags(pend, np, epoch);
     }
 }
 
