@@ -1,0 +1,150 @@
+# VoronoiRTB200.jl — the Julia-side binding a VoronoiRT maintainer adds to route the irregular-grid hot path
+# through libvrt.so.  Same function names and signatures as the reference (src/voronoi_utils.jl:36,
+# src/irregular_ray_tracing.jl:15,96, src/lambda_iteration.jl:60,207, src/rates.jl:154, src/populations.jl:191), so the
+# entry scripts (compare_searchlight.jl, compare_continuum.jl, compare_line.jl) run unchanged after
+#     include("VoronoiRTB200.jl"); using .VoronoiRTB200
+# NOTE: no Julia toolchain exists in the build image, so this file has not been executed here; it is the
+# documented ccall stub for include/vrt.h (see INTEGRATION.md).  The Python mirror voronoirt_b200/api.py makes exactly
+# the same calls and is what the parity tests drive.
+module VoronoiRTB200
+
+using Unitful
+
+const libvrt = get(ENV, "LIBVRT", joinpath(@__DIR__, "..", "voronoirt_b200", "libvrt.so"))
+
+struct VRTError <: Exception
+    code::Cint
+    msg::String
+end
+check(rc::Cint) = rc == 0 ? nothing : throw(VRTError(rc, unsafe_string(ccall((:vrt_last_error, libvrt), Cstring, ()))))
+
+# ---------------------------------------------------------------- structs of include/vrt.h
+struct vrt_line
+    nlam::Int64
+    lidx::NTuple{4,Int64}
+    lambda0::Float64
+    Aji::Float64; Bji::Float64; Bij::Float64
+    chi_i::Float64; chi_j::Float64; chi_inf::Float64
+    gi::Int64; gj::Int64; Z::Int64
+    atom_weight::Float64
+    c_unsold::Float64; gamma_natural::Float64; c_linear_stark::Float64; c_quadratic_stark::Float64
+end
+struct vrt_site_data
+    temperature::Ptr{Float64}; electron_density::Ptr{Float64}; hydrogen_density::Ptr{Float64}
+    velocity_z::Ptr{Float64}; velocity_x::Ptr{Float64}; velocity_y::Ptr{Float64}; doppler_width::Ptr{Float64}
+    alpha_cont::Ptr{Float64}; destruction::Ptr{Float64}; C::Ptr{Float64}; lte_pops::Ptr{Float64}
+end
+struct vrt_quadrature
+    n_dirs::Int64
+    weights::Ptr{Float64}; theta::Ptr{Float64}; phi::Ptr{Float64}
+end
+struct vrt_config
+    n_sweeps::Int32; reserved0::Int32
+    p::Float64
+    lam_begin::Int64; lam_end::Int64; lam_chunk::Int64
+    prune::Int32; tile_cells::Int32
+end
+struct vrt_result
+    iterations::Int32; converged::Int32
+    diff::Float64; seconds::Float64
+end
+
+# ---------------------------------------------------------------- read_cell (src/voronoi_utils.jl:36-85)
+mutable struct Grid
+    h::Ptr{Cvoid}
+    n::Int
+end
+const GRIDS = IdDict{Any,Grid}()      # NeighbourMatrix -> device grid built from it
+
+function read_cell(fname::String, n_sites::Int, positions::Matrix{<:Unitful.Length},
+                   x_min, x_max, y_min, y_max)
+    ld = Ref{Int64}(0)
+    check(ccall((:vrt_read_neighbours, libvrt), Cint, (Cstring, Int64, Ptr{Int64}, Int64, Ref{Int64}), fname, n_sites, C_NULL, 0, ld))
+    NeighbourMatrix = zeros(Int64, n_sites, ld[])
+    check(ccall((:vrt_read_neighbours, libvrt), Cint, (Cstring, Int64, Ptr{Int64}, Int64, Ref{Int64}), fname, n_sites, NeighbourMatrix, ld[], ld))
+    pos = ustrip.(u"m", positions)
+    bounds = Float64[0, 0, ustrip(u"m", x_min), ustrip(u"m", x_max), ustrip(u"m", y_min), ustrip(u"m", y_max)]
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:vrt_grid_create, libvrt), Cint, (Int64, Ptr{Float64}, Ptr{Int64}, Int64, Ptr{Float64}, Ref{Ptr{Cvoid}}),
+                n_sites, pos, NeighbourMatrix, ld[], bounds, h))
+    g = Grid(h[], n_sites)
+    finalizer(x -> ccall((:vrt_grid_destroy, libvrt), Cvoid, (Ptr{Cvoid},), x.h), g)
+    GRIDS[NeighbourMatrix] = g
+    layers(down) = begin
+        L = Ref{Int64}(0)
+        check(ccall((:vrt_grid_num_layers, libvrt), Cint, (Ptr{Cvoid}, Int32, Ref{Int64}), g.h, down, L))
+        perm = Vector{Int64}(undef, n_sites); off = Vector{Int64}(undef, L[] + 1)
+        check(ccall((:vrt_grid_get_layers, libvrt), Cint, (Ptr{Cvoid}, Int32, Ptr{Int64}, Ptr{Int64}), g.h, down, perm, off))
+        perm, off
+    end
+    perm_up, layers_up = layers(0)
+    perm_down, layers_down = layers(1)
+    Delaunay_lines = Array{Float64,3}(undef, 3, ld[] - 1, n_sites)
+    check(ccall((:vrt_grid_get_delaunay_lines, libvrt), Cint, (Ptr{Cvoid}, Ptr{Float64}), g.h, Delaunay_lines))
+    return positions, NeighbourMatrix, Delaunay_lines, layers_up, layers_down, perm_up, perm_down
+end
+
+grid_of(sites) = GRIDS[sites.neighbours]
+
+# ---------------------------------------------------------------- Delaunay_upII / Delaunay_downII (src/irregular_ray_tracing.jl)
+function _formal(k, S, I_0, α, sites, n_sweeps, p, down)
+    Sv = ustrip.(u"kW*m^-2*nm^-1", S); αv = ustrip.(u"m^-1", α); I0v = ustrip.(u"kW*m^-2*nm^-1", I_0)
+    nlam = ndims(Sv) == 1 ? 1 : size(Sv, 1)
+    I = similar(Sv)
+    check(ccall((:vrt_formal_solve, libvrt), Cint,
+                (Ptr{Cvoid}, Ptr{Float64}, Int32, Float64, Int32, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+                grid_of(sites).h, Float64.(k), down, p, n_sweeps, nlam, Sv, αv, I0v, I))
+    return I * u"kW*m^-2*nm^-1"
+end
+Delaunay_upII(k, S, I_0, α, sites, n_sweeps::Int, p::Float64=7.0) = _formal(k, S, I_0, α, sites, n_sweeps, p, 0)
+Delaunay_downII(k, S, I_0, α, sites, n_sweeps::Int, p::Float64=7.0) = _formal(k, S, I_0, α, sites, n_sweeps, p, 1)
+
+# ---------------------------------------------------------------- Λ_voronoi (src/lambda_iteration.jl:207-297)
+# The host computes the Transparency.jl quantities exactly as the reference does before its loop (:216-247) and hands
+# them over; the loop itself (J_λ_voronoi, S update, calculate_R, get_revised_populations, criterion) runs on the GPU.
+function Λ_voronoi(ϵ::AbstractFloat, maxiter::Integer, sites, line, quadrature::String, DATA::String;
+                   LTE_pops, α_cont, ελ, C, line_struct::vrt_line, on_iteration=nothing)
+    tab = readdlm_quadrature(quadrature)                       # weights θ ϕ (functions.jl:33-63; the table, not the path, crosses the ABI)
+    w, th, ph = tab[:, 1], tab[:, 2], tab[:, 3]
+    q = Ref(vrt_quadrature(length(w), pointer(w), pointer(th), pointer(ph)))
+    cfg = Ref(vrt_config(3, 0, 7.0, 0, 0, 0, 1, 0))
+    vec(x, u) = Float64.(ustrip.(u, x))
+    T = vec(sites.temperature, u"K"); ne = vec(sites.electron_density, u"m^-3"); NH = vec(sites.hydrogen_populations, u"m^-3")
+    vz = vec(sites.velocity_z, u"m/s"); vx = vec(sites.velocity_x, u"m/s"); vy = vec(sites.velocity_y, u"m/s")
+    dD = vec(line.ΔD, u"nm"); ac = vec(α_cont, u"m^-1"); el = Float64.(ελ); Cv = vec(C, u"s^-1"); lte = vec(LTE_pops, u"m^-3")
+    lam = vec(line.λ, u"nm")
+    sd = Ref(vrt_site_data(pointer(T), pointer(ne), pointer(NH), pointer(vz), pointer(vx), pointer(vy), pointer(dD),
+                           pointer(ac), pointer(el), pointer(Cv), pointer(lte)))
+    s = Ref{Ptr{Cvoid}}(C_NULL)
+    res = Ref(vrt_result(0, 0, 0.0, 0.0))
+    n, nλ = sites.n, length(lam)
+    S = Matrix{Float64}(undef, nλ, n); J = similar(S); pops = Matrix{Float64}(undef, n, 3)
+    GC.@preserve w th ph T ne NH vz vx vy dD ac el Cv lte lam begin
+        check(ccall((:vrt_solver_create_line, libvrt), Cint,
+                    (Ptr{Cvoid}, Ref{vrt_line}, Ptr{Float64}, Ref{vrt_site_data}, Ref{vrt_quadrature}, Ref{vrt_config}, Ref{Ptr{Cvoid}}),
+                    grid_of(sites).h, Ref(line_struct), lam, sd, q, cfg, s))
+        # per-iteration hook: the reference writes populations and S to its HDF5 file every iteration (:280-281)
+        cb = on_iteration === nothing ? C_NULL : @cfunction($on_iteration, Cint, (Ptr{Cvoid}, Ptr{Cvoid}))
+        check(ccall((:vrt_lambda_iterate, libvrt), Cint, (Ptr{Cvoid}, Float64, Int32, Ptr{Cvoid}, Ptr{Cvoid}, Ref{vrt_result}),
+                    s[], ϵ, maxiter, cb, C_NULL, res))
+        check(ccall((:vrt_get_state, libvrt), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}), s[], S, J, pops))
+        ccall((:vrt_solver_destroy, libvrt), Cvoid, (Ptr{Cvoid},), s[])
+    end
+    return J * u"kW*m^-2*nm^-1", S * u"kW*m^-2*nm^-1", α_cont, pops * u"m^-3"
+end
+
+# get_revised_populations (src/populations.jl:191-221)
+function get_revised_populations(R::Array{<:Unitful.Frequency,3}, C::Array{<:Unitful.Frequency,3}, atom_density::Vector)
+    n = length(atom_density)
+    pops = Matrix{Float64}(undef, n, 3)
+    check(ccall((:vrt_get_revised_populations, libvrt), Cint, (Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+                n, ustrip.(u"s^-1", R), ustrip.(u"s^-1", C), ustrip.(u"m^-3", atom_density), pops))
+    return pops * u"m^-3"
+end
+
+function readdlm_quadrature(fname)
+    rows = [parse.(Float64, split(l)) for l in eachline(fname) if !isempty(strip(l))]
+    return permutedims(hcat(rows...))
+end
+
+end # module

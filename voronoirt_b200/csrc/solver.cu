@@ -123,26 +123,48 @@ struct OpacityDirs {
 };
 
 // compute_voigt_profile (line.jl:121-137) + αline_λ (line.jl:219-225) + α_cont, for every direction of the batch.
-// grid-stride over (cell, λ); the direction loop is innermost so the per-(cell,λ) quantities are shared.
-__global__ void k_opacity(int64_t n, int64_t lc, const double* __restrict__ lam /* chunk */, LineDev L, const OpacityDirs D,
-                          const double* __restrict__ gamma, const double* __restrict__ dD, const double* __restrict__ vz,
-                          const double* __restrict__ vx, const double* __restrict__ vy, const double* __restrict__ pops,
-                          const double* __restrict__ alpha_cont) {
-    int64_t total = n * lc;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        int64_t c = i / lc, l = i - c * lc;
-        double lm = lam[l];
-        double dd = dD[c];
-        double a = damping_param(gamma[c], lm, dd);
-        double pop = pops[c] * L.Bij - pops[n + c] * L.Bji;
-        double ac = alpha_cont[c];
-        double v0 = vz[c], v1 = vx[c], v2 = vy[c];
+// A CTA owns a tile of OP_TC cells x all lc wavelengths.  The math runs with the 32 lanes of a warp on 32 DIFFERENT
+// CELLS at the SAME wavelength: the Humlíček region (|v| + a) is then almost warp-uniform, whereas lanes over
+// wavelengths (core .. far wing) would serialise all four regions.  The tile is transposed through shared memory
+// so that the α rows go out as coalesced fp64 row writes.
+constexpr int OP_TC = 32;
+constexpr int OP_THREADS = 256;
+__global__ void __launch_bounds__(OP_THREADS) k_opacity(int64_t n, int64_t lc, const double* __restrict__ lam /* chunk */, LineDev L,
+                                                        const OpacityDirs D, const double* __restrict__ gamma,
+                                                        const double* __restrict__ dD, const double* __restrict__ vz,
+                                                        const double* __restrict__ vx, const double* __restrict__ vy,
+                                                        const double* __restrict__ pops, const double* __restrict__ alpha_cont) {
+    extern __shared__ double tile[];                 // [OP_TC][ldt]
+    const int ldt = (int)lc | 1;                     // odd row stride: conflict-light transposed writes
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = OP_THREADS / 32;
+    for (int64_t c0 = (int64_t)blockIdx.x * OP_TC; c0 < n; c0 += (int64_t)gridDim.x * OP_TC) {
+        const int64_t c = c0 + lane;
+        const bool ok = c < n;
+        const int64_t cc = ok ? c : n - 1;
+        const double dd = dD[cc], g = gamma[cc];
+        const double pop = pops[cc] * L.Bij - pops[n + cc] * L.Bji;
+        const double ac = alpha_cont[cc];
+        const double v0 = vz[cc], v1 = vx[cc], v2 = vy[cc];
+        const int ncell = (int)min((int64_t)OP_TC, n - c0);
         for (int d = 0; d < D.nd; d++) {
             // line_of_sight_velocity(sites, -k) (line.jl:198-208); explicitly rounded like the oracle
-            double vlos = __dadd_rn(__dadd_rn(__dmul_rn(v0, -D.k[d][0]), __dmul_rn(v1, -D.k[d][1])), __dmul_rn(v2, -D.k[d][2]));
-            double v = __ddiv_rn(__dadd_rn(__dadd_rn(lm, -L.lambda0), __ddiv_rn(__dmul_rn(L.lambda0, vlos), C_0)), dd);
-            double prof = voigt_profile(a, v, dd * 1e-9);
-            D.alpha[d][i] = L.c_line * prof * pop + ac;
+            const double vlos = __dadd_rn(__dadd_rn(__dmul_rn(v0, -D.k[d][0]), __dmul_rn(v1, -D.k[d][1])), __dmul_rn(v2, -D.k[d][2]));
+            const double shift = __ddiv_rn(__dmul_rn(L.lambda0, vlos), C_0);
+            for (int l = warp; l < lc; l += nwarp) {
+                const double lm = lam[l];
+                const double a = damping_param(g, lm, dd);
+                const double v = __ddiv_rn(__dadd_rn(__dadd_rn(lm, -L.lambda0), shift), dd);
+                const double prof = voigt_profile(a, v, dd * 1e-9);
+                tile[lane * ldt + l] = L.c_line * prof * pop + ac;
+            }
+            __syncthreads();
+            double* __restrict__ out = D.alpha[d] + c0 * lc;
+            const int total = ncell * (int)lc;
+            for (int i = threadIdx.x; i < total; i += OP_THREADS) {
+                const int r = i / (int)lc, l = i - r * (int)lc;
+                out[i] = tile[r * ldt + l];
+            }
+            __syncthreads();
         }
     }
 }
@@ -600,8 +622,13 @@ static int mean_intensity_internal(vrt_solver* s, SweepStats* stats, double* t_o
             }
             if (s->is_line) {
                 VRT_CUDA(cudaEventRecord(e0));
-                k_opacity<<<nblocks(n * lc, 256), 256>>>(n, lc, s->lam_dev.p + s->l_begin + l0, s->ld, od, s->gamma.p, s->dD.p, s->vz.p,
-                                                         s->vx.p, s->vy.p, s->pops.p, s->alpha_cont.p);
+                {
+                    const size_t shm = sizeof(double) * OP_TC * (size_t)((int)lc | 1);
+                    const int grid = (int)std::min<int64_t>((n + OP_TC - 1) / OP_TC, 148 * 16);
+                    if (shm > 48 * 1024) VRT_CUDA(cudaFuncSetAttribute(k_opacity, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
+                    k_opacity<<<grid, OP_THREADS, shm>>>(n, lc, s->lam_dev.p + s->l_begin + l0, s->ld, od, s->gamma.p, s->dD.p, s->vz.p,
+                                                        s->vx.p, s->vy.p, s->pops.p, s->alpha_cont.p);
+                }
                 VRT_CUDA(cudaEventRecord(e1));
                 stats->kernels += 1;
             }
