@@ -8,8 +8,9 @@ Bifrost-shaped Voronoi grid (BASELINE.json metric: cell·angle·freq updates/s p
 A "step" is one full Λ-iteration (opacity + formal solution over all directions and wavelengths + source update
 + radiative rates + statistical equilibrium + criterion).  `value` = n_sites·n_dirs·n_λ / (time per step), inputs
 resident in HBM; `e2e` = the same through the C ABI with pinned HOST buffers (state in, S/J/populations out, every
-step).  N > 1 (torchrun): wavelengths are sharded over the ranks, one NCCL all-reduce of the radiative rates and one
-of the criterion per iteration; the total problem is fixed ("strong" scaling).
+step).  N > 1 (torchrun): the quadrature directions (and, beyond the direction count, the wavelengths) are sharded over
+the ranks, each holding the full grid; one NCCL all-reduce of J (plus the rates when wavelengths are sharded, plus the
+scalar criterion) per iteration; the total problem is fixed ("strong" scaling).
 --impl reference times the CPU oracle (a port of the reference's Julia algorithm; Julia itself is not installed)
 on a bounded sample of the same workload with all host threads.
 """
@@ -69,6 +70,14 @@ def build_problem(workload):
         atm = {k: np.tile(v, kx * ky) for k, v in atm.items()}
     return dict(pos=pos, nbr=nbr, bounds=bounds, atm=atm, n=pos.shape[1], qpath=api.quadrature_path(qname), qname=qname,
                 nbb=nbb, nbf=nbf, tiles=(kx, ky), base=base)
+
+
+def shard_grid(world, ndirs):
+    """world = D direction shards x G wavelength shards, D as large as the direction count allows"""
+    D = world
+    while D > 1 and (D > ndirs or world % D):
+        D -= 1
+    return D, world // D
 
 
 def shard_range(nlam, world, rank):
@@ -211,6 +220,7 @@ def main():
     dist = None
     if world > 1:
         import torch.distributed as dist
+        os.environ["NCCL_DEBUG"] = "WARN"   # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     t_setup = time.time()
@@ -218,26 +228,44 @@ def main():
     atm, b, n = P["atm"], P["bounds"], P["n"]
     line, lte, α_cont, ελ, Cr = synth.line_inputs(atm["temperature"], atm["electron_density"], atm["hydrogen_density"], P["nbb"], P["nbf"])
     nlam = len(line.λ)
-    lo, hi = shard_range(nlam, world, rank)
+    w, th, ph, nq = V.read_quadrature(P["qpath"])
+    # multi-GPU decomposition: D direction shards x G wavelength shards (D*G = world).  Directions first: the sweep's cost
+    # is per (cell, direction) visit, so fewer directions per GPU scales it, narrower wavelength rows barely do.
+    D, G = shard_grid(world, int(nq))
+    di, gi = rank % D, rank // D
+    lo, hi = shard_range(nlam, G, gi)
+    dlo, dhi = shard_range(int(nq), D, di)
     cell = V.read_cell(P["nbr"], n, P["pos"], b["x_min"], b["x_max"], b["y_min"], b["y_max"])
     sites = V.VoronoiSites(*cell, atm["temperature"], atm["electron_density"], atm["hydrogen_density"], atm["velocity_z"],
                            atm["velocity_x"], atm["velocity_y"], b["z_min"], b["z_max"], b["x_min"], b["x_max"], b["y_min"], b["y_max"], n)
-    w, th, ph, nq = V.read_quadrature(P["qpath"])
     ndirs = int(np.sum(th != 90))
     solver = V.Solver(sites, P["qpath"], line=line, α_cont=α_cont, ελ=ελ, C_rates=Cr, LTE_pops=lte,
-                      lam_range=(lo, hi) if world > 1 else None)
+                      lam_range=(lo, hi) if G > 1 else None, dir_range=(dlo, dhi) if D > 1 else None)
     if world > 1:
         class _Dev:
             def __init__(self, ptr, count):
                 self.__cuda_array_interface__ = {"shape": (count,), "typestr": "<f8", "data": (ptr, False), "version": 3}
 
+        # process groups: ranks sharing a direction shard (they differ in wavelength shard) and vice versa
+        lam_groups = [dist.new_group([g * D + d for g in range(G)]) for d in range(D)]
+        dir_groups = [dist.new_group([g * D + d for d in range(D)]) for g in range(G)]
+
         def allreduce(ptr, count, op):
+            if op == 0 and G == 1:
+                return 0        # the rates are already complete: this rank holds every wavelength
+            if op == 2 and D == 1:
+                return 0
             t = torch.as_tensor(_Dev(ptr, count), device=torch.device("cuda", local_rank))
-            dist.all_reduce(t, op=dist.ReduceOp.MAX if op == 1 else dist.ReduceOp.SUM)
+            if op == 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            elif op == 0:
+                dist.all_reduce(t, op=dist.ReduceOp.SUM, group=lam_groups[di])
+            else:
+                dist.all_reduce(t, op=dist.ReduceOp.SUM, group=dir_groups[gi])
             torch.cuda.synchronize()
             return 0
         solver.set_allreduce(allreduce)
-    log(f"setup {time.time() - t_setup:.1f}s: n={n} dirs={ndirs} nlam={nlam} shard=[{lo},{hi}) layers up/down={len(sites.layers_up) - 1}/{len(sites.layers_down) - 1}")
+    log(f"setup {time.time() - t_setup:.1f}s: n={n} dirs={ndirs} nlam={nlam} shards: {D} direction x {G} wavelength; rank 0 has directions [{dlo},{dhi}) wavelengths [{lo},{hi}) layers up/down={len(sites.layers_up) - 1}/{len(sites.layers_down) - 1}")
 
     def sync():
         torch.cuda.synchronize()
@@ -268,7 +296,7 @@ def main():
 
     # ---- roofline of the dominant kernel (k_sweep): algorithmic bytes / measured kernel time (CUDA events in the library)
     B_alg = 40.0 + 104.0 / nlam
-    local_updates = float(n) * ndirs * (hi - lo)
+    local_updates = float(n) * int(np.sum(th[dlo:dhi] != 90)) * (hi - lo)
     launches = max(stats["kernels"], 1)
     achieved = B_alg * local_updates * K / (stats["sweep_ms"] / 1e3) / 1e9 if stats["sweep_ms"] > 0 else 0.0
     peak, peak_src = measured_peak()
@@ -297,10 +325,18 @@ def main():
         import ctypes as C
         L = _lib.lib()
 
+        null_cb = _abi_null_cb()
+        dbg = os.environ.get("VRT_DEBUG")
+
         def step():
+            ta = time.perf_counter()
             _lib.check(L.vrt_set_state(solver.h, C.c_void_p(hS.data_ptr()), C.c_void_p(hP.data_ptr())))
-            _lib.check(L.vrt_lambda_iterate(solver.h, -1.0, 1, _abi_null_cb(), None, None))
+            tb = time.perf_counter()
+            _lib.check(L.vrt_lambda_iterate(solver.h, -1.0, 1, null_cb, None, None))
+            tc = time.perf_counter()
             _lib.check(L.vrt_get_state(solver.h, C.c_void_p(hS.data_ptr()), C.c_void_p(hJ.data_ptr()), C.c_void_p(hP.data_ptr())))
+            if dbg:
+                log(f"e2e step: set_state {1e3 * (tb - ta):.1f} ms, iterate {1e3 * (tc - tb):.1f} ms, get_state {1e3 * (time.perf_counter() - tc):.1f} ms")
         for _ in range(2):
             step()
         sync()
@@ -335,7 +371,7 @@ def main():
                "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "strong",
                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                "config": {"workload": workload_name(args.workload, P, nlam), "sites": n, "quadrature": P["qname"], "n_dirs": ndirs, "n_lambda": nlam,
-                          "parallelism": f"lambda-shard x{world}" if world > 1 else "single GPU", "l2_policy": "inputs larger than L2 "
+                          "parallelism": f"{D} direction shards x {G} wavelength shards, NCCL all-reduce of J ({8 * n * (hi - lo) / 1e6:.0f} MB) per iteration" if world > 1 else "single GPU", "l2_policy": "inputs larger than L2 "
                           f"(S+J+I+alpha = {8 * n * nlam * (2 + 2 * ndirs) / 1e9:.1f} GB)", "n_sweeps": 3, "p": 7.0},
                "s_per_lambda_iteration": ms_max / K / 1e3, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
                "gpu_launches": int(launches), "clocks": clocks,

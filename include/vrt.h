@@ -89,17 +89,19 @@ typedef struct vrt_quadrature {
 
 typedef struct vrt_config {
     int32_t n_sweeps;        /* in-layer Gauss–Seidel sweeps; the reference hard-wires 3 (lambda_iteration.jl:82) */
-    int32_t reserved0;
+    int32_t dir_begin;       /* direction shard [dir_begin, dir_end) of the quadrature table owned by this process; */
     double p;                /* upwind weighting exponent, `const p = 7.0` (irregular_ray_tracing.jl:1) */
     int64_t lam_begin;       /* wavelength shard [lam_begin, lam_end) owned by this process, 0-based;   */
     int64_t lam_end;         /*   0,0 = all wavelengths                                                  */
     int64_t lam_chunk;       /* wavelengths swept together per pass (0 = choose from free HBM)          */
     int32_t prune;           /* 1 = skip re-sweeps of cells whose value cannot change (exact), 0 = visit every cell n_sweeps times */
-    int32_t tile_cells;      /* cells per work tile (0 = default)                                       */
+    int32_t dir_end;         /*   0,0 = all directions (J is then this shard's partial sum unless an all-reduce hook is set) */
 } vrt_config;
 
-/* all-reduce hook for the wavelength-sharded multi-GPU path: called with a DEVICE buffer of `count`
- * doubles that must be reduced in place over all shards (op 0 = sum, 1 = max). */
+/* all-reduce hook of the multi-GPU path: called with a DEVICE buffer of `count` doubles that must be reduced in place.
+ *   op 0: sum over the processes that own the same direction shard (i.e. over the wavelength shards): radiative rates;
+ *   op 1: max over all processes: convergence criterion;
+ *   op 2: sum over the processes that own the same wavelength shard (i.e. over the direction shards): mean intensity J. */
 typedef int (*vrt_allreduce_fn)(void* dev_buf, int64_t count, int32_t op, void* user);
 
 /* per-iteration report handed to the host callback (replaces the println/HDF5 hooks at

@@ -39,10 +39,10 @@ struct vrt_quadrature
     weights::Ptr{Float64}; theta::Ptr{Float64}; phi::Ptr{Float64}
 end
 struct vrt_config
-    n_sweeps::Int32; reserved0::Int32
+    n_sweeps::Int32; dir_begin::Int32
     p::Float64
     lam_begin::Int64; lam_end::Int64; lam_chunk::Int64
-    prune::Int32; tile_cells::Int32
+    prune::Int32; dir_end::Int32
 end
 struct vrt_result
     iterations::Int32; converged::Int32

@@ -388,3 +388,21 @@ def test_errors_are_reported_not_raised_across_the_abi(V):
     rc = L.vrt_grid_create(4, C.c_void_p(pos.ctypes.data), C.c_void_p(nbr.ctypes.data), 3, C.c_void_p(b.ctypes.data), C.byref(h))
     assert rc == -4
     assert b"not connected" in L.vrt_last_error()
+
+
+def test_direction_shards_sum_to_full_J(V, oracle):
+    """two direction shards in one process: the partial mean intensities add up to the unsharded J (what the op-2 all-reduce does)"""
+    from voronoirt_b200 import atom
+    P = line_problem(V, oracle, "grid_unit300", nbb=10, nbf=4)
+    line, sites = P["line"], P["sites"]
+    qp = V.quadrature_path("ul7n12")
+    S = np.asfortranarray(atom.B_λ(line.λ[:, None], sites.temperature[None, :]))
+    full = V.Solver(sites, qp, line=line, α_cont=P["α_cont"], LTE_pops=P["lte"])
+    Jf = full.mean_intensity(S, P["lte"])
+    full.close()
+    Jsum = np.zeros_like(Jf)
+    for lo, hi in ((0, 5), (5, 12)):
+        sh = V.Solver(sites, qp, line=line, α_cont=P["α_cont"], LTE_pops=P["lte"], dir_range=(lo, hi))
+        Jsum += sh.mean_intensity(S, P["lte"])
+        sh.close()
+    assert rel_err(Jsum, Jf) < 1e-13

@@ -38,10 +38,10 @@ class vrt_quadrature(C.Structure):
 
 class vrt_config(C.Structure):
     _fields_ = [
-        ("n_sweeps", C.c_int32), ("reserved0", C.c_int32),
+        ("n_sweeps", C.c_int32), ("dir_begin", C.c_int32),
         ("p", C.c_double),
         ("lam_begin", C.c_int64), ("lam_end", C.c_int64), ("lam_chunk", C.c_int64),
-        ("prune", C.c_int32), ("tile_cells", C.c_int32),
+        ("prune", C.c_int32), ("dir_end", C.c_int32),
     ]
 
 

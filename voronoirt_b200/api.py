@@ -230,7 +230,7 @@ class Solver:
     """vrt_solver handle (state of Λ_voronoi).  kind: 'line' or 'continuum'."""
 
     def __init__(self, sites, quadrature, line=None, α_cont=None, ελ=None, C_rates=None, LTE_pops=None, B_0=None,
-                 n_sweeps=3, p=7.0, lam_range=None, lam_chunk=0, prune=1):
+                 n_sweeps=3, p=7.0, lam_range=None, lam_chunk=0, prune=1, dir_range=None):
         self.sites = sites
         self.line = line
         q = _as_quadrature(quadrature)
@@ -238,6 +238,8 @@ class Solver:
         cfg.n_sweeps, cfg.p, cfg.prune, cfg.lam_chunk = n_sweeps, p, prune, lam_chunk
         if lam_range is not None:
             cfg.lam_begin, cfg.lam_end = lam_range
+        if dir_range is not None:
+            cfg.dir_begin, cfg.dir_end = dir_range
         h = C.c_void_p()
         n = sites.n
         self._keep = []
@@ -296,7 +298,8 @@ class Solver:
         check(lib().vrt_solver_set_field(self.h, self.FIELDS[name], _ptr(a)))
 
     def set_allreduce(self, fn):
-        """fn(dev_ptr:int, count:int, op:int) -> 0 on success; op 0 = sum, 1 = max"""
+        """fn(dev_ptr:int, count:int, op:int) -> 0 on success; op 0 = sum over wavelength shards, 1 = max over all,
+        2 = sum over direction shards (include/vrt.h)"""
         def tramp(ptr, count, op, user):
             try:
                 return int(fn(ptr, count, op) or 0)
@@ -422,7 +425,7 @@ def Λ_voronoi(ϵ, maxiter, sites, *args, **kw):
     if len(args) >= 2 and not isinstance(args[0], (str, bytes, tuple, list)):
         line, quadrature = args[0], args[1]
         s = Solver(sites, quadrature, line=line, α_cont=kw["α_cont"], ελ=kw["ελ"], C_rates=kw["C"], LTE_pops=kw["LTE_pops"],
-                   **{k: v for k, v in kw.items() if k in ("n_sweeps", "p", "lam_range", "lam_chunk", "prune")})
+                   **{k: v for k, v in kw.items() if k in ("n_sweeps", "p", "lam_range", "lam_chunk", "prune", "dir_range")})
         try:
             res = s.iterate(ϵ, maxiter, callback)
             S, J, pops = s.get_state()

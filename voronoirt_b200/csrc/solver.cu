@@ -440,6 +440,7 @@ struct vrt_solver {
     // state
     DevBuf<double> S, J, pops, Rp, S_prev;
     bool have_state = false;
+    bool dir_sharded = false;
     bool gamma_valid = false;
     // work buffers of the current (λ-chunk, direction-batch) plan
     int64_t lc = 0;
@@ -482,7 +483,17 @@ static int solver_common_init(vrt_solver* s, vrt_grid* g, const vrt_quadrature* 
     VRT_CUDA(cudaMemcpy(w.data(), quad->weights, sizeof(double) * quad->n_dirs, cudaMemcpyDefault));
     VRT_CUDA(cudaMemcpy(th.data(), quad->theta, sizeof(double) * quad->n_dirs, cudaMemcpyDefault));
     VRT_CUDA(cudaMemcpy(ph.data(), quad->phi, sizeof(double) * quad->n_dirs, cudaMemcpyDefault));
-    for (int64_t i = 0; i < quad->n_dirs; i++) {
+    int64_t d_lo = 0, d_hi = quad->n_dirs;
+    if (c.dir_end > c.dir_begin) {
+        if (c.dir_begin < 0 || c.dir_end > quad->n_dirs) {
+            set_error("solver: direction shard out of range");
+            return VRT_E_INVALID;
+        }
+        d_lo = c.dir_begin;
+        d_hi = c.dir_end;
+        s->dir_sharded = true;
+    }
+    for (int64_t i = d_lo; i < d_hi; i++) {
         double t = th[i], p = ph[i];
         // k = [cosθ, cosϕ sinθ, sinϕ sinθ] (lambda_iteration.jl:87); θ == 90 is skipped by both branches (:98,:104)
         if (!(t > 90) && !(t < 90)) continue;
@@ -645,6 +656,15 @@ static int mean_intensity_internal(vrt_solver* s, SweepStats* stats, double* t_o
         }
     }
     VRT_CUDA(cudaDeviceSynchronize());
+    if (s->dir_sharded && s->allreduce) {
+        // J = sum over the direction shards (lambda_iteration.jl:102,107 add the directions one after the other)
+        if (s->nd == 0) VRT_CUDA(cudaMemset(s->J.p, 0, sizeof(double) * (size_t)n * s->nlam));
+        int rc = s->allreduce(s->J.p, n * s->nlam, 2, s->allreduce_user);
+        if (rc != 0) {
+            set_error("all-reduce hook failed (%d)", rc);
+            return VRT_E_STATE;
+        }
+    }
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     if (t_opacity_ms) *t_opacity_ms = opacity_ms;
