@@ -37,6 +37,7 @@ struct SweepParams {
     int nlam;
     int cv;                  // visits per chunk
     int32_t epoch;
+    int32_t run_len;         // visits per producer run (<= 32)
     int32_t experiment;      // VRT_EXPERIMENT: timing experiments only (0 in production)
     unsigned long long* prof; // experiment 2: per-role cycle counters
 };
@@ -328,7 +329,7 @@ __global__ void __launch_bounds__(32 * (TMA_NP + TMA_NC), 3) k_sweep_tma(const S
         const long long nblk = gridDim.x;
         unsigned it = 0;                  // chunks handed to the consumers so far
         unsigned rc = 0;                  // runs of this CTA so far
-        const int RL = 32;
+        const int RL = P.run_len;
         const double* __restrict__ S = P.S;
         const int64_t ldS = P.ldS;
         const int G = P.T * P.nd;
@@ -350,17 +351,8 @@ __global__ void __launch_bounds__(32 * (TMA_NP + TMA_NC), 3) k_sweep_tma(const S
                     const unsigned my = it + (unsigned)lane;
                     const int stage = (int)(my % (unsigned)ns);
                     const uint32_t round = my / (unsigned)ns;
-                    long long c0 = 0, c1 = 0, c2 = 0;
-                    if (P.experiment == 2) { volatile uint32_t touch = v.b.z; (void)touch; c0 = clock64(); }
                     wait_flags2(D->flags, v.b.z, v.b.w, epoch);
-                    if (P.experiment == 2) c1 = clock64();
-                    while (consumed[stage] != round) __nanosleep(32);
-                    if (P.experiment == 2) {
-                        c2 = clock64();
-                        atomicAdd(P.prof + 0, (unsigned long long)(c1 - c0));   // producer lane: flag waits
-                        atomicAdd(P.prof + 1, (unsigned long long)(c2 - c1));   // producer lane: stage waits
-                        atomicAdd(P.prof + 2, 1ull);
-                    }
+                    asm volatile("fence.proxy.async;" ::: "memory");   // the flags were acquired through the generic proxy
                     // rows of the stage: 0 α_c, 1 S_c, 2 α_u1, 3 S_u1, 4 I_u1, 5 α_u2, 6 S_u2, 7 I_u2
                     const double* src[8];
                     const double* alpha = D->alpha;
@@ -394,9 +386,10 @@ __global__ void __launch_bounds__(32 * (TMA_NP + TMA_NC), 3) k_sweep_tma(const S
                     h.valid = 1;
                     h.seq = my;
                     h.pad = 0;
+                    // take the stage as late as possible: its lifetime bounds the throughput of the ring
+                    while (consumed[stage] != round) __nanosleep(32);
                     hdr[stage] = h;
                     mbar_arrive_expect_tx(full + stage, tot);
-                    asm volatile("fence.proxy.async;" ::: "memory");   // the flags were acquired through the generic proxy
 #pragma unroll
                     for (int r = 0; r < 8; r++) {
                         if (src[r]) {
@@ -571,6 +564,7 @@ int sweep_run(vrt_grid* g, int nd, const SweepDir* dirs, const double* S, int64_
     P.nlam = (int)nlam;
     P.cv = cv;
     P.epoch = epoch;
+    P.run_len = getenv("VRT_RUN_LEN") ? std::max(1, std::min(32, atoi(getenv("VRT_RUN_LEN")))) : 32;
     P.experiment = getenv("VRT_EXPERIMENT") ? atoi(getenv("VRT_EXPERIMENT")) : 0;
     DevBuf<unsigned long long> d_prof;
     VRT_TRY(d_prof.alloc(16));
