@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define VRT_ABI_VERSION 1
+#define VRT_ABI_VERSION 2
 
 enum {
     VRT_OK = 0,
@@ -96,12 +96,18 @@ typedef struct vrt_config {
     int64_t lam_chunk;       /* wavelengths swept together per pass (0 = choose from free HBM)          */
     int32_t prune;           /* 1 = skip re-sweeps of cells whose value cannot change (exact), 0 = visit every cell n_sweeps times */
     int32_t dir_end;         /*   0,0 = all directions (J is then this shard's partial sum unless an all-reduce hook is set) */
+    int32_t cell_shard_rank; /* with direction shards: position of this process among the cell_shard_count processes that share */
+    int32_t cell_shard_count;/*   its wavelength shard.  When > 1, vrt_lambda_iterate reduce-scatters J over cells (hook op 3), runs the
+                              *   source update, rates and statistical equilibrium on its own cell slice only, and all-gathers S and the
+                              *   populations (hook op 4).  0 = every process does these for all cells after an all-reduce of J. */
 } vrt_config;
 
 /* all-reduce hook of the multi-GPU path: called with a DEVICE buffer of `count` doubles that must be reduced in place.
  *   op 0: sum over the processes that own the same direction shard (i.e. over the wavelength shards): radiative rates;
  *   op 1: max over all processes: convergence criterion;
- *   op 2: sum over the processes that own the same wavelength shard (i.e. over the direction shards): mean intensity J. */
+ *   op 2: sum over the processes that own the same wavelength shard (i.e. over the direction shards): mean intensity J;
+ *   op 3: reduce-scatter (sum) over the same group as op 2: the buffer is cell_shard_count equal slices, on return slice
+ *         cell_shard_rank holds the sum;   op 4: all-gather over that group: slice r is valid on rank r, all slices on return. */
 typedef int (*vrt_allreduce_fn)(void* dev_buf, int64_t count, int32_t op, void* user);
 
 /* per-iteration report handed to the host callback (replaces the println/HDF5 hooks at

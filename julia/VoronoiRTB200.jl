@@ -43,6 +43,7 @@ struct vrt_config
     p::Float64
     lam_begin::Int64; lam_end::Int64; lam_chunk::Int64
     prune::Int32; dir_end::Int32
+    cell_shard_rank::Int32; cell_shard_count::Int32
 end
 struct vrt_result
     iterations::Int32; converged::Int32
@@ -107,7 +108,7 @@ function Λ_voronoi(ϵ::AbstractFloat, maxiter::Integer, sites, line, quadrature
     tab = readdlm_quadrature(quadrature)                       # weights θ ϕ (functions.jl:33-63; the table, not the path, crosses the ABI)
     w, th, ph = tab[:, 1], tab[:, 2], tab[:, 3]
     q = Ref(vrt_quadrature(length(w), pointer(w), pointer(th), pointer(ph)))
-    cfg = Ref(vrt_config(3, 0, 7.0, 0, 0, 0, 1, 0))
+    cfg = Ref(vrt_config(3, 0, 7.0, 0, 0, 0, 1, 0, 0, 0))
     vec(x, u) = Float64.(ustrip.(u, x))
     T = vec(sites.temperature, u"K"); ne = vec(sites.electron_density, u"m^-3"); NH = vec(sites.hydrogen_populations, u"m^-3")
     vz = vec(sites.velocity_z, u"m/s"); vx = vec(sites.velocity_x, u"m/s"); vy = vec(sites.velocity_y, u"m/s")

@@ -42,6 +42,7 @@ class vrt_config(C.Structure):
         ("p", C.c_double),
         ("lam_begin", C.c_int64), ("lam_end", C.c_int64), ("lam_chunk", C.c_int64),
         ("prune", C.c_int32), ("dir_end", C.c_int32),
+        ("cell_shard_rank", C.c_int32), ("cell_shard_count", C.c_int32),
     ]
 
 

@@ -230,7 +230,7 @@ class Solver:
     """vrt_solver handle (state of Λ_voronoi).  kind: 'line' or 'continuum'."""
 
     def __init__(self, sites, quadrature, line=None, α_cont=None, ελ=None, C_rates=None, LTE_pops=None, B_0=None,
-                 n_sweeps=3, p=7.0, lam_range=None, lam_chunk=0, prune=1, dir_range=None):
+                 n_sweeps=3, p=7.0, lam_range=None, lam_chunk=0, prune=1, dir_range=None, cell_shard=None):
         self.sites = sites
         self.line = line
         q = _as_quadrature(quadrature)
@@ -240,6 +240,8 @@ class Solver:
             cfg.lam_begin, cfg.lam_end = lam_range
         if dir_range is not None:
             cfg.dir_begin, cfg.dir_end = dir_range
+        if cell_shard is not None:
+            cfg.cell_shard_rank, cfg.cell_shard_count = cell_shard
         h = C.c_void_p()
         n = sites.n
         self._keep = []
@@ -299,7 +301,7 @@ class Solver:
 
     def set_allreduce(self, fn):
         """fn(dev_ptr:int, count:int, op:int) -> 0 on success; op 0 = sum over wavelength shards, 1 = max over all,
-        2 = sum over direction shards (include/vrt.h)"""
+        2 = sum over direction shards, 3 = reduce-scatter / 4 = all-gather over direction shards (include/vrt.h)"""
         def tramp(ptr, count, op, user):
             try:
                 return int(fn(ptr, count, op) or 0)

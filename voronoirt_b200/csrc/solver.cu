@@ -286,7 +286,8 @@ struct RateLam {           // per local wavelength, host-precomputed
 };
 
 // one warp per cell, lanes over the shard's wavelengths; out: Rp[6][n] = R12,R21,R13,R31,R23,R32
-__global__ void k_rates(int64_t n, int64_t nlam, const RateLam* __restrict__ rl, LineDev L, const double* __restrict__ T,
+// n = cells handled (pointers already offset to the first of them), stride = cell stride of the SoA arrays lte / Rp
+__global__ void k_rates(int64_t n, int64_t stride, int64_t nlam, const RateLam* __restrict__ rl, LineDev L, const double* __restrict__ T,
                         const double* __restrict__ dD, const double* __restrict__ gamma, const double* __restrict__ damping /* or null */,
                         const double* __restrict__ lte /* [3][n] */, const double* __restrict__ J, double* __restrict__ Rp) {
     const int lane = threadIdx.x & 31;
@@ -297,7 +298,7 @@ __global__ void k_rates(int64_t n, int64_t nlam, const RateLam* __restrict__ rl,
     for (int64_t c = warp; c < n; c += nwarps) {
         double acc[6] = {0, 0, 0, 0, 0, 0};
         double Tc = T[c], dd = dD[c];
-        double n1 = lte[c], n2 = lte[n + c], n3 = lte[2 * n + c];
+        double n1 = lte[c], n2 = lte[stride + c], n3 = lte[2 * stride + c];
         double r0 = n1 / n2, r1 = n1 / n3, r2 = n2 / n3;
         double sc = hc / (4 * PI * (L.lambda0 * 1e-9)) * L.Bij;
         for (int64_t l = lane; l < nlam; l += 32) {
@@ -326,7 +327,7 @@ __global__ void k_rates(int64_t n, int64_t nlam, const RateLam* __restrict__ rl,
         for (int k = 0; k < 6; k++)
             for (int o = 16; o > 0; o >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
         if (lane == 0)
-            for (int k = 0; k < 6; k++) Rp[(int64_t)k * n + c] = acc[k];
+            for (int k = 0; k < 6; k++) Rp[(int64_t)k * stride + c] = acc[k];
     }
 }
 
@@ -361,17 +362,30 @@ __device__ __forceinline__ void stat_eq_site(double P12, double P21, double P13,
 }
 
 // internal SoA version: Rp, Cp [6][n] (12,21,13,31,23,32), pops [3][n]
-__global__ void k_stateq_soa(int64_t n, const double* __restrict__ Rp, const double* __restrict__ Cp, const double* __restrict__ NH,
-                             double* __restrict__ pops) {
+__global__ void k_stateq_soa(int64_t n, int64_t stride, const double* __restrict__ Rp, const double* __restrict__ Cp,
+                             const double* __restrict__ NH, double* __restrict__ pops) {
     int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (c >= n) return;
     double P[6];
-    for (int k = 0; k < 6; k++) P[k] = Rp[(int64_t)k * n + c] + Cp[(int64_t)k * n + c];
+    for (int k = 0; k < 6; k++) P[k] = Rp[(int64_t)k * stride + c] + Cp[(int64_t)k * stride + c];
     double n1, n2, n3;
     stat_eq_site(P[0], P[1], P[2], P[3], P[4], P[5], NH[c], n1, n2, n3);
     pops[c] = n1;
-    pops[n + c] = n2;
-    pops[2 * n + c] = n3;
+    pops[stride + c] = n2;
+    pops[2 * stride + c] = n3;
+}
+
+// populations of a cell slice [c0, c0+cs) <-> packed [3][cs] block (the unit of the all-gather over cell shards)
+__global__ void k_pack_pops(int64_t n, int64_t c0, int64_t cs, const double* __restrict__ pops, double* __restrict__ blk) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= cs) return;
+    for (int k = 0; k < 3; k++) blk[(int64_t)k * cs + i] = (c0 + i < n) ? pops[(int64_t)k * n + c0 + i] : 0.0;
+}
+__global__ void k_unpack_pops(int64_t n, int64_t cs, int R, const double* __restrict__ all, double* __restrict__ pops) {
+    int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (c >= n) return;
+    int64_t r = c / cs, i = c - r * cs;
+    for (int k = 0; k < 3; k++) pops[(int64_t)k * n + c] = all[(r * 3 + k) * cs + i];
 }
 
 // ABI version: R, C 3 x 3 x n (column-major, [a + 3b + 9i] = M[a+1,b+1,i+1]), pops n x 3
@@ -441,6 +455,9 @@ struct vrt_solver {
     DevBuf<double> S, J, pops, Rp, S_prev;
     bool have_state = false;
     bool dir_sharded = false;
+    int cell_R = 1, cell_r = 0;             // cell shards of the post-J stages (source, rates, stat-eq)
+    int64_t cs = 0, c0 = 0, c1 = 0, n_pad = 0; // cells per shard, own slice [c0, c1), padded cell count
+    DevBuf<double> pops_blk;
     bool gamma_valid = false;
     // work buffers of the current (λ-chunk, direction-batch) plan
     int64_t lc = 0;
@@ -474,6 +491,19 @@ static int solver_common_init(vrt_solver* s, vrt_grid* g, const vrt_quadrature* 
         if (c.p == 0.0) c.p = 7.0;
     }
     s->cfg = c;
+    s->cell_R = 1; s->cell_r = 0;
+    if (c.cell_shard_count > 1) {
+        if (c.cell_shard_rank < 0 || c.cell_shard_rank >= c.cell_shard_count) {
+            set_error("solver: cell shard rank out of range");
+            return VRT_E_INVALID;
+        }
+        s->cell_R = c.cell_shard_count;
+        s->cell_r = c.cell_shard_rank;
+    }
+    s->cs = (g->n + s->cell_R - 1) / s->cell_R;
+    s->n_pad = s->cs * s->cell_R;
+    s->c0 = std::min<int64_t>(g->n, s->cs * s->cell_r);
+    s->c1 = std::min<int64_t>(g->n, s->c0 + s->cs);
     const int cv = chunk_visits(c.lam_chunk > 0 ? std::min<int64_t>(c.lam_chunk, nlam_local) : nlam_local);
     if (!quad || quad->n_dirs <= 0 || !quad->weights || !quad->theta || !quad->phi) {
         set_error("solver: bad quadrature");
@@ -596,7 +626,8 @@ static int plan_buffers(vrt_solver* s) {
 }
 
 // J_λ_voronoi on device state: s->S -> s->J (internal order)
-static int mean_intensity_internal(vrt_solver* s, SweepStats* stats, double* t_opacity_ms, double* t_sweep_ms) {
+// scatter: false = all-reduce J over the direction shards (every rank gets the full J); true = reduce-scatter over cells
+static int mean_intensity_internal(vrt_solver* s, SweepStats* stats, double* t_opacity_ms, double* t_sweep_ms, bool scatter = false) {
     const int64_t n = s->n;
     VRT_TRY(plan_buffers(s));
     cudaEvent_t e0, e1;
@@ -666,7 +697,8 @@ static int mean_intensity_internal(vrt_solver* s, SweepStats* stats, double* t_o
     if (s->dir_sharded && s->allreduce) {
         // J = sum over the direction shards (lambda_iteration.jl:102,107 add the directions one after the other)
         if (s->nd == 0) VRT_CUDA(cudaMemset(s->J.p, 0, sizeof(double) * (size_t)n * s->nlam));
-        int rc = s->allreduce(s->J.p, n * s->nlam, 2, s->allreduce_user);
+        int rc = scatter ? s->allreduce(s->J.p, s->n_pad * s->nlam, 3, s->allreduce_user)
+                         : s->allreduce(s->J.p, n * s->nlam, 2, s->allreduce_user);
         if (rc != 0) {
             set_error("all-reduce hook failed (%d)", rc);
             return VRT_E_STATE;
@@ -679,7 +711,7 @@ static int mean_intensity_internal(vrt_solver* s, SweepStats* stats, double* t_o
     return VRT_OK;
 }
 
-static int rates_internal(vrt_solver* s, const double* damping_int) {
+static int rates_internal(vrt_solver* s, const double* damping_int, int64_t c0, int64_t c1) {
     const int64_t n = s->n;
     if (!s->lte.p) {
         set_error("radiative rates need the LTE populations (vrt_site_data.lte_pops or vrt_solver_set_field)");
@@ -692,7 +724,11 @@ static int rates_internal(vrt_solver* s, const double* damping_int) {
     int64_t warps_needed = n;
     int bs = 256;
     int64_t blocks = std::min<int64_t>((warps_needed * 32 + bs - 1) / bs, 148 * 64);
-    k_rates<<<(int)blocks, bs>>>(n, s->nlam, s->rl.p, s->ld, s->T.p, s->dD.p, s->gamma.p, damping_int, s->lte.p, s->J.p, s->Rp.p);
+    {
+        const int64_t cn = c1 - c0;   // own cell slice (all cells unless cell-sharded)
+        k_rates<<<(int)blocks, bs>>>(cn, n, s->nlam, s->rl.p, s->ld, s->T.p + c0, s->dD.p + c0, s->gamma.p + c0,
+                                     damping_int ? damping_int + c0 * s->nlam : nullptr, s->lte.p + c0, s->J.p + c0 * s->nlam, s->Rp.p + c0);
+    }
     VRT_CUDA(cudaGetLastError());
     if (s->allreduce) {
         VRT_CUDA(cudaDeviceSynchronize());
@@ -896,9 +932,10 @@ int vrt_solver_create_line(vrt_grid* g, const vrt_line* line, const double* lamb
     if (sd->C) VRT_TRY(set_field(s, VRT_FIELD_C, sd->C));
     if (sd->lte_pops) VRT_TRY(set_field(s, VRT_FIELD_LTE_POPS, sd->lte_pops));
     VRT_TRY(s->gamma.alloc(n));
-    VRT_TRY(s->S.alloc((size_t)n * s->nlam + 2)); VRT_TRY(s->J.alloc((size_t)n * s->nlam));
+    VRT_TRY(s->S.alloc((size_t)s->n_pad * s->nlam + 2)); VRT_TRY(s->J.alloc((size_t)s->n_pad * s->nlam));
     VRT_TRY(s->pops.alloc((size_t)3 * n)); VRT_TRY(s->Rp.alloc((size_t)6 * n));
-    VRT_CUDA(cudaMemset(s->J.p, 0, sizeof(double) * (size_t)n * s->nlam));
+    VRT_CUDA(cudaMemset(s->J.p, 0, sizeof(double) * (size_t)s->n_pad * s->nlam));
+    VRT_CUDA(cudaMemset(s->S.p, 0, sizeof(double) * ((size_t)s->n_pad * s->nlam + 2)));
 
     // per-wavelength rate constants (σic rates.jl:422-438, gaunt_bf :562-572, trapezoid weights)
     {
@@ -1055,7 +1092,7 @@ int vrt_calculate_R(vrt_solver* s, const double* J, const double* damping, doubl
         VRT_TRY(upload_rows(s->g, damping, dmp.p, s->nlam, s->stage));
         dmp_int = dmp.p;
     }
-    VRT_TRY(rates_internal(s, dmp_int));
+    VRT_TRY(rates_internal(s, dmp_int, 0, n));
     DevBuf<double> tmp;
     double* out = R;
     if (!is_device_ptr(R)) {
@@ -1107,27 +1144,47 @@ int vrt_lambda_iterate(vrt_solver* s, double eps, int32_t maxiter, vrt_iter_cb c
     VRT_TRY(read_diff(s, &diff));
     int i = 0;
     SweepStats total;
+    // post-J stages on this rank's cell slice only (reduce-scatter of J, all-gather of S and populations)
+    const bool cshard = s->cell_R > 1 && s->dir_sharded && s->allreduce && s->is_line;
+    const int64_t c0 = cshard ? s->c0 : 0, c1 = cshard ? s->c1 : n, cn = c1 - c0;
     while (diff > eps && i < maxiter) {
         auto t0 = std::chrono::steady_clock::now();
         SweepStats stats;
         vrt_iter_info info;
         memset(&info, 0, sizeof(info));
         info.diff = diff;
-        VRT_TRY(mean_intensity_internal(s, &stats, &info.t_opacity_ms, &info.t_sweep_ms));
+        VRT_TRY(mean_intensity_internal(s, &stats, &info.t_opacity_ms, &info.t_sweep_ms, cshard));
         cudaEvent_t e[4];
         for (auto& ev : e) VRT_CUDA(cudaEventCreate(&ev));
         VRT_CUDA(cudaMemset(s->diff_bits.p, 0, sizeof(unsigned long long)));
         VRT_CUDA(cudaMemset(s->diff_nan.p, 0, sizeof(int)));
         VRT_CUDA(cudaEventRecord(e[0]));
-        k_source_update<<<nblocks(n * s->nlam, 256), 256>>>(n, s->nlam, s->lam_dev.p + s->l_begin, s->T.p, s->is_line ? nullptr : s->B0.p,
-                                                            s->eps.p, s->J.p, s->S.p, use_thick, s->diff_bits.p, s->diff_nan.p);
+        if (cn > 0)
+            k_source_update<<<nblocks(cn * s->nlam, 256), 256>>>(cn, s->nlam, s->lam_dev.p + s->l_begin, s->T.p + c0,
+                                                                 s->is_line ? nullptr : s->B0.p + c0, s->eps.p + c0, s->J.p + c0 * s->nlam,
+                                                                 s->S.p + c0 * s->nlam, use_thick, s->diff_bits.p, s->diff_nan.p);
         VRT_CUDA(cudaEventRecord(e[1]));
         stats.kernels += 1;
         if (s->is_line) {
-            VRT_TRY(rates_internal(s, nullptr));
+            VRT_TRY(rates_internal(s, nullptr, c0, c1));
             VRT_CUDA(cudaEventRecord(e[2]));
-            k_stateq_soa<<<nblocks(n, 256), 256>>>(n, s->Rp.p, s->Cp.p, s->NH.p, s->pops.p);
+            if (cn > 0) k_stateq_soa<<<nblocks(cn, 256), 256>>>(cn, n, s->Rp.p + c0, s->Cp.p + c0, s->NH.p + c0, s->pops.p + c0);
             VRT_CUDA(cudaEventRecord(e[3]));
+            stats.kernels += 2;
+        }
+        if (cshard) {
+            // every rank now owns S and the populations of its cell slice: all-gather both over the direction group
+            VRT_TRY(s->pops_blk.ensure((size_t)3 * s->n_pad));
+            k_pack_pops<<<nblocks(s->cs, 256), 256>>>(n, s->cs * s->cell_r, s->cs, s->pops.p, s->pops_blk.p + (size_t)3 * s->cs * s->cell_r);
+            VRT_CUDA(cudaGetLastError());
+            VRT_CUDA(cudaDeviceSynchronize());
+            int rc = s->allreduce(s->pops_blk.p, 3 * s->n_pad, 4, s->allreduce_user);
+            if (rc == 0) rc = s->allreduce(s->S.p, s->n_pad * s->nlam, 4, s->allreduce_user);
+            if (rc != 0) {
+                set_error("all-gather hook failed (%d)", rc);
+                return VRT_E_STATE;
+            }
+            k_unpack_pops<<<nblocks(n, 256), 256>>>(n, s->cs, s->cell_R, s->pops_blk.p, s->pops.p);
             stats.kernels += 2;
         }
         VRT_CUDA(cudaGetLastError());
@@ -1165,7 +1222,16 @@ int vrt_get_state(vrt_solver* s, double* S, double* J, double* populations) {
     VRT_TRY(ensure_state(s));
     const int64_t n = s->n;
     if (S) VRT_TRY(download_rows(s->g, s->S.p, S, s->nlam, s->stage));
-    if (J) VRT_TRY(download_rows(s->g, s->J.p, J, s->nlam, s->stage));
+    if (J) {
+        if (s->cell_R > 1 && s->dir_sharded && s->allreduce && s->is_line) {   // J lives as cell slices: gather it (collective call)
+            int rc = s->allreduce(s->J.p, s->n_pad * s->nlam, 4, s->allreduce_user);
+            if (rc != 0) {
+                set_error("all-gather hook failed (%d)", rc);
+                return VRT_E_STATE;
+            }
+        }
+        VRT_TRY(download_rows(s->g, s->J.p, J, s->nlam, s->stage));
+    }
     if (populations && s->is_line) {
         DevBuf<double> tmp;
         double* o = populations;

@@ -268,9 +268,10 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     uint32_t done;
     const uint32_t addr = smem_u32(bar);
+    // the suspend-time hint keeps a waiting warp parked in hardware instead of re-issuing the try_wait every few cycles
     do {
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(addr), "r"(parity), "r"(2000u) : "memory");
     } while (!done);
 }
 __device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
@@ -287,7 +288,7 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint3
 
 constexpr int TMA_MAX_STAGES = 32;
 #ifndef TMA_DEFER
-#define TMA_DEFER 6
+#define TMA_DEFER 12
 #endif
 
 // TMA_NP producer warps (independent issue chains) + TMA_NC consumer warps per CTA
@@ -387,7 +388,7 @@ __global__ void __launch_bounds__(32 * (TMA_NP + TMA_NC), 3) k_sweep_tma(const S
                     h.seq = my;
                     h.pad = 0;
                     // take the stage as late as possible: its lifetime bounds the throughput of the ring
-                    while (consumed[stage] != round) __nanosleep(32);
+                    while (consumed[stage] != round) __nanosleep(100);
                     hdr[stage] = h;
                     mbar_arrive_expect_tx(full + stage, tot);
 #pragma unroll
