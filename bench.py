@@ -240,12 +240,16 @@ def main():
     D, G = shard_grid(world, int(nq))
     di, gi = rank % D, rank // D
     lo, hi = shard_range(nlam, G, gi)
-    dlo, dhi = shard_range(int(nq), D, di)
+    # directions are dealt round-robin (rank di takes di, di+D, ...): neighbouring lines of the quadrature files are up/down
+    # pairs of similar inclination, so every rank gets a similar mix of cheap (steep) and expensive (grazing) directions
+    mine = list(range(di, int(nq), D))
+    my_quad = (w[mine], th[mine], ph[mine]) if D > 1 else P["qpath"]
+    dlo, dhi = 0, len(mine)
     cell = V.read_cell(P["nbr"], n, P["pos"], b["x_min"], b["x_max"], b["y_min"], b["y_max"])
     sites = V.VoronoiSites(*cell, atm["temperature"], atm["electron_density"], atm["hydrogen_density"], atm["velocity_z"],
                            atm["velocity_x"], atm["velocity_y"], b["z_min"], b["z_max"], b["x_min"], b["x_max"], b["y_min"], b["y_max"], n)
     ndirs = int(np.sum(th != 90))
-    solver = V.Solver(sites, P["qpath"], line=line, α_cont=α_cont, ελ=ελ, C_rates=Cr, LTE_pops=lte,
+    solver = V.Solver(sites, my_quad, line=line, α_cont=α_cont, ελ=ελ, C_rates=Cr, LTE_pops=lte,
                       lam_range=(lo, hi) if G > 1 else None, dir_range=(dlo, dhi) if D > 1 else None,
                       cell_shard=(di, D) if D > 1 and not os.environ.get("VRT_NO_CELL_SHARD") else None)
     coll = {"ms": 0.0, "bytes": 0}
@@ -286,7 +290,7 @@ def main():
             coll["bytes"] += 8 * count
             return 0
         solver.set_allreduce(allreduce)
-    log(f"setup {time.time() - t_setup:.1f}s: n={n} dirs={ndirs} nlam={nlam} shards: {D} direction x {G} wavelength; rank 0 has directions [{dlo},{dhi}) wavelengths [{lo},{hi}) layers up/down={len(sites.layers_up) - 1}/{len(sites.layers_down) - 1}")
+    log(f"setup {time.time() - t_setup:.1f}s: n={n} dirs={ndirs} nlam={nlam} shards: {D} direction x {G} wavelength; rank 0 has directions {mine} wavelengths [{lo},{hi}) layers up/down={len(sites.layers_up) - 1}/{len(sites.layers_down) - 1}")
 
     def sync():
         torch.cuda.synchronize()
@@ -319,7 +323,7 @@ def main():
 
     # ---- roofline of the dominant kernel (k_sweep): algorithmic bytes / measured kernel time (CUDA events in the library)
     B_alg = 40.0 + 104.0 / nlam
-    local_updates = float(n) * int(np.sum(th[dlo:dhi] != 90)) * (hi - lo)
+    local_updates = float(n) * int(np.sum(th[mine] != 90)) * (hi - lo)
     launches = max(stats["kernels"], 1)
     achieved = B_alg * local_updates * K / (stats["sweep_ms"] / 1e3) / 1e9 if stats["sweep_ms"] > 0 else 0.0
     peak, peak_src = measured_peak()
