@@ -34,6 +34,7 @@ WORKLOADS = {
     # name: (base sites tessellated by voro++, tiles in x, tiles in y, quadrature, nλ_bb, nλ_bf)
     "small": (20000, 1, 1, "ul7n12", 50, 20),
     "nlte_1m": (250000, 2, 2, "ul7n12", 50, 20),
+    "nlte_1m_direct": (1000000, 1, 1, "ul7n12", 50, 20),   # 1 M sites tessellated directly (no tiling): slower set-up, same solve
     "nlte_4m": (250000, 4, 4, "ul9n20", 50, 20),
     "nlte_16m": (250000, 8, 8, "ul9n20", 50, 20),
 }
