@@ -231,3 +231,18 @@ def B_lambda(lam_nm, T):
 
 def num_threads():
     return lib().orc_num_threads()
+
+
+def short_characteristics(z, x, y, k, down, S, I_0, alpha, n_sweeps=3):
+    """characteristics.jl:19-180.  S, alpha: (nz, nx, ny) Fortran-ordered (Julia layout, ghost columns included);
+    I_0: (nx, ny) -> (I (nz, nx, ny) Fortran-ordered, plane branch per z (1 xy, 2 yz, 3 xz))"""
+    z, x, y, k = map(f64, (z, x, y, k))
+    S = np.asfortranarray(S, dtype=np.float64)
+    alpha = np.asfortranarray(alpha, dtype=np.float64)
+    I_0 = np.asfortranarray(I_0, dtype=np.float64)
+    nz, nx, ny = S.shape
+    out = np.zeros((nz, nx, ny), order="F")
+    planes = np.zeros(nz, dtype=np.int32)
+    lib().orc_short_characteristics(C.c_int64(nz), C.c_int64(nx), C.c_int64(ny), _p(z), _p(x), _p(y), _p(k), C.c_int(down),
+                                    _p(S), _p(I_0), _p(alpha), C.c_int(n_sweeps), _p(out), _p(planes))
+    return out, planes
