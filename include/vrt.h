@@ -178,6 +178,22 @@ int vrt_grid_get_schedule(vrt_grid* g, const double k[3], int32_t down, int32_t 
 int vrt_formal_solve(vrt_grid* g, const double k[3], int32_t down, double p, int32_t n_sweeps,
                      int64_t nlam, const double* S, const double* alpha, const double* I0, double* I_out);
 
+/* ---------------------------------------------------------------- regular-grid formal solver */
+
+/* short_characteristics_up (down=0, characteristics.jl:19-95) / short_characteristics_down (down=1, :110-180) with
+ * their six ray routines (:191-835), batched over nlam independent wavelengths.  z, x, y: the Atmosphere axes
+ * (atmosphere.jl:22-31), x and y INCLUDING the periodic ghost columns, as the reference holds them.  S, alpha,
+ * I_out: nlam x nz x nx x ny column-major (wavelength fastest; for nlam = 1 exactly the Julia (nz, nx, ny) array);
+ * I0: nlam x nx x ny, the boundary plane (z[0] for up, z[nz-1] for down).  plane_branch (optional, nz int32) receives the
+ * ray routine taken per plane: 1 xy, 2 yz, 3 xz, 0 for the boundary plane (argmin at :52-56).  nx, ny <= 1026. */
+int vrt_regular_formal_solve(int64_t nz, int64_t nx, int64_t ny, const double* z, const double* x, const double* y,
+                             const double k[3], int32_t down, int32_t n_sweeps, int64_t nlam, const double* S,
+                             const double* alpha, const double* I0, double* I_out, int32_t* plane_branch);
+
+/* vrt_regular_formal_solve keeps its device workspace (3-4 internal copies of one wavelength chunk) between calls;
+ * this frees it, e.g. before handing the GPU to an irregular-grid solver. */
+int vrt_regular_release_workspace(void);
+
 /* ---------------------------------------------------------------- Λ-iteration engine */
 
 /* NLTE line solver state (Λ_voronoi, lambda_iteration.jl:207-297). lambda: nlam wavelengths, nm. */

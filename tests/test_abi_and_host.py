@@ -66,6 +66,11 @@ def test_no_cpu_fallback_compute_fails_loudly_without_a_device():
     assert rc == -2 and b"CUDA" in L.vrt_last_error()      # VRT_E_CUDA, never a silent CPU path
     with pytest.raises(_lib.VRTError):
         _lib.check(rc)
+    # the regular-grid entry as well
+    import voronoirt_b200 as V
+    ax = np.linspace(0, 1, 6)
+    with pytest.raises(_lib.VRTError, match="CUDA"):
+        V.short_characteristics_up(V.direction(160, 45), np.zeros((6, 6, 6)), np.zeros((6, 6)), np.zeros((6, 6, 6)), V.Atmosphere(ax, ax, ax))
 
 
 def test_product_never_touches_the_oracle():

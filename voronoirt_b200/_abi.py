@@ -81,6 +81,9 @@ PROTOTYPES = {
     "vrt_grid_get_stencil": (C.c_int, [C.c_void_p, P, C.c_double, P, P, P, P]),
     "vrt_grid_get_schedule": (C.c_int, [C.c_void_p, P, C.c_int32, C.c_int32, C.c_int32, P, P, P, c_int64_p, c_int64_p]),
     "vrt_formal_solve": (C.c_int, [C.c_void_p, P, C.c_int32, C.c_double, C.c_int32, C.c_int64, P, P, P, P]),
+    "vrt_regular_formal_solve": (C.c_int, [C.c_int64, C.c_int64, C.c_int64, P, P, P, P, C.c_int32, C.c_int32, C.c_int64,
+                                           P, P, P, P, P]),
+    "vrt_regular_release_workspace": (C.c_int, []),
     "vrt_solver_create_line": (C.c_int, [C.c_void_p, C.POINTER(vrt_line), P, C.POINTER(vrt_site_data),
                                          C.POINTER(vrt_quadrature), C.POINTER(vrt_config), C.POINTER(C.c_void_p)]),
     "vrt_solver_create_continuum": (C.c_int, [C.c_void_p, P, P, P, C.POINTER(vrt_quadrature),

@@ -215,6 +215,53 @@ def Delaunay_downII(k, S, I_0, α, sites, n_sweeps, p=7.0):
     return _formal(k, S, I_0, α, sites, n_sweeps, p, 1)
 
 
+# ------------------------------------------------------------------ characteristics.jl (regular grid)
+class Atmosphere:
+    """src/atmosphere.jl:22-31 (same field names and order); x and y carry the periodic ghost columns."""
+
+    def __init__(self, z, x, y, temperature=None, electron_density=None, hydrogen_populations=None,
+                 velocity_z=None, velocity_x=None, velocity_y=None):
+        self.z, self.x, self.y = (np.ascontiguousarray(a, dtype=np.float64) for a in (z, x, y))
+        self.temperature, self.electron_density, self.hydrogen_populations = temperature, electron_density, hydrogen_populations
+        self.velocity_z, self.velocity_x, self.velocity_y = velocity_z, velocity_x, velocity_y
+
+
+def _short_characteristics(k, S_0, I_0, α, atmos, n_sweeps, down, return_branches=False):
+    nz, nx, ny = len(atmos.z), len(atmos.x), len(atmos.y)
+    S_0 = _f(S_0)
+    α = _f(α)
+    I_0 = _f(I_0)
+    if S_0.ndim == 3:
+        nlam = 1
+        if S_0.shape != (nz, nx, ny) or α.shape != (nz, nx, ny) or I_0.shape != (nx, ny):
+            raise ValueError("S_0, α must be (nz, nx, ny) and I_0 (nx, ny)")
+    else:
+        nlam = S_0.shape[0]
+        if S_0.shape != (nlam, nz, nx, ny) or α.shape != S_0.shape or I_0.shape != (nlam, nx, ny):
+            raise ValueError("S_0, α must be (nλ, nz, nx, ny) and I_0 (nλ, nx, ny)")
+    out = np.zeros_like(S_0, order="F")
+    branch = np.zeros(nz, dtype=np.int32)
+    k = np.ascontiguousarray(k, dtype=np.float64)
+    check(lib().vrt_regular_formal_solve(nz, nx, ny, _ptr(atmos.z), _ptr(atmos.x), _ptr(atmos.y), _ptr(k), down, int(n_sweeps), nlam,
+                                         _ptr(S_0), _ptr(α), _ptr(I_0), _ptr(out), _ptr(branch)))
+    return (out, branch) if return_branches else out
+
+
+def regular_release_workspace():
+    """free the device workspace vrt_regular_formal_solve keeps between calls"""
+    check(lib().vrt_regular_release_workspace())
+
+
+def short_characteristics_up(k, S_0, I_0, α, atmos, n_sweeps=3, return_branches=False):
+    """src/characteristics.jl:19-95.  S_0, α: (nz, nx, ny) or (nλ, nz, nx, ny); I_0: (nx, ny) or (nλ, nx, ny)."""
+    return _short_characteristics(k, S_0, I_0, α, atmos, n_sweeps, 0, return_branches)
+
+
+def short_characteristics_down(k, S_0, I_0, α, atmos, n_sweeps=3, return_branches=False):
+    """src/characteristics.jl:110-180."""
+    return _short_characteristics(k, S_0, I_0, α, atmos, n_sweeps, 1, return_branches)
+
+
 # ------------------------------------------------------------------ Λ-iteration engine
 def _as_quadrature(quadrature):
     if isinstance(quadrature, (str, bytes)):
