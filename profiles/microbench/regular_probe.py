@@ -38,7 +38,10 @@ out = torch.empty_like(S)
 branch = np.zeros(nz, dtype=np.int32)
 L = _lib.lib()
 rows = []
-for theta, phi in ((152.7, 315.5), (70.3, 346.4), (78.2, 55.4), (27.3, 135.5)):
+DIRS = ((152.7, 315.5), (70.3, 346.4), (78.2, 55.4), (27.3, 135.5))
+if os.environ.get('VRT_PROBE_DIRS'):
+    DIRS = [DIRS[int(i)] for i in os.environ['VRT_PROBE_DIRS'].split(',')]
+for theta, phi in DIRS:
     k = np.ascontiguousarray(V.direction(theta, phi))
     down = int(theta < 90)
     ms = []

@@ -196,7 +196,8 @@ __global__ void k_reg_coef(RegPlane P, int up, double zc, double zb1, double zb2
 
 __device__ __forceinline__ double reg_ldg(const double* p) {
     double v;
-    asm("ld.global.nc.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    asm volatile("ld.volatile.global.f64 %0, [%1];" : "=d"(v) : "l"(p));   // ld.volatile: ptxas keeps it where it is written
+                                                                            // (plain loads sink to the end of the unrolled group)
     return v;
 }
 __device__ __forceinline__ void reg_stg(double* p, double v) { asm volatile("st.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory"); }
@@ -213,15 +214,17 @@ template <int MAXT>
 __global__ void __launch_bounds__(MAXT) k_reg_rec(RegPlane P, int n_sweeps, const double* __restrict__ cA,
                                                    const double* __restrict__ cB, const double* __restrict__ cC,
                                                    double* __restrict__ Iout) {
-    extern __shared__ double car[];   // 2 x np
+    extern __shared__ double car[];   // 2 x np carried rows
     const int np = P.np, ns = P.ns, nsi = P.ns - 2;
-    const int j = threadIdx.x + 1;
-    const bool active = j <= np - 2;
+    // threads past the last interior column repeat it (same values to the same addresses) instead of idling behind a
+    // predicate that would be re-evaluated in every step
+    const int j = min((int)threadIdx.x + 1, np - 2);
     const size_t base = (size_t)blockIdx.x * np * ns;
     const int off = (P.sgn_j + 1) / 2;
-    const int il = reg_wrap(active ? j - off : 1, np), iu = reg_wrap(active ? j - off + 1 : 1, np);
-    const int o0 = (P.sgn_s > 0 ? 1 : ns - 2) * np, stride = P.sgn_s * np;   // element offsets inside the plane (< 2^20)
+    const int il = reg_wrap(j - off, np), iu = reg_wrap(j - off + 1, np);
+    const int o0 = (P.sgn_s > 0 ? 1 : ns - 2) * np, stride = P.sgn_s * np;   // element offsets inside the plane (< 2^21)
     const int total = n_sweeps * nsi, last0 = total - nsi;
+    const int o_end = o0 + stride * nsi;
     for (int q = threadIdx.x; q < 2 * np; q += blockDim.x) car[q] = 0.0;
     const double* pA = cA + base + j;
     const double* pB = cB + base + j;
@@ -231,34 +234,38 @@ __global__ void __launch_bounds__(MAXT) k_reg_rec(RegPlane P, int n_sweeps, cons
     asm volatile("" : "+l"(pA), "+l"(pB), "+l"(pC), "+l"(pI));
     int il1 = il + np, iu1 = iu + np, jw0 = j, jw1 = j + np, il0 = il, iu0 = iu;
     asm volatile("" : "+r"(il0), "+r"(iu0), "+r"(il1), "+r"(iu1), "+r"(jw0), "+r"(jw1));
-    int so = o0, cnt = 0;       // row being solved
-    int po = o0, cpf = 0;       // row being prefetched (wraps into the next sweep; past the end it re-reads valid rows)
+    __syncthreads();
     double a[REG_PF], b[REG_PF], c[REG_PF];
+    int po = o0, so = o0;   // rows being prefetched / solved; both wrap into the next sweep
 #pragma unroll
     for (int d = 0; d < REG_PF; d++) {
-        a[d] = b[d] = c[d] = 0.0;
-        if (active) { a[d] = reg_ldg(pA + po); b[d] = reg_ldg(pB + po); c[d] = reg_ldg(pC + po); }
-        if (++cpf == nsi) { cpf = 0; po = o0; } else po += stride;
+        a[d] = reg_ldg(pA + po); b[d] = reg_ldg(pB + po); c[d] = reg_ldg(pC + po);
+        po += stride;
+        if (po == o_end) po = o0;
     }
-    __syncthreads();
-    for (int t0 = 0; t0 < total; t0 += REG_PF) {
+    // one row step; REG_PF is even, so the parity of tt is the parity of d and the double buffer is indexed statically
+#define REG_STEP(d, tt)                                                                                     \
+    {                                                                                                       \
+        const double v = ((d)&1) ? fma(a[d], car[il1], fma(b[d], car[iu1], c[d]))                           \
+                                 : fma(a[d], car[il0], fma(b[d], car[iu0], c[d]));                          \
+        if ((d)&1) car[jw0] = v; else car[jw1] = v;                                                         \
+        a[d] = reg_ldg(pA + po); b[d] = reg_ldg(pB + po); c[d] = reg_ldg(pC + po);                          \
+        if ((tt) >= last0) reg_stg(pI + so, v);                                                             \
+        po += stride;                                                                                       \
+        if (po == o_end) po = o0;                                                                           \
+        so += stride;                                                                                       \
+        if (so == o_end) so = o0;                                                                           \
+        __syncthreads();                                                                                    \
+    }
+    int t0 = 0;
+    for (; t0 + REG_PF <= total; t0 += REG_PF) {
 #pragma unroll
-        for (int d = 0; d < REG_PF; d++) {
-            const int tt = t0 + d;
-            if (tt < total) {   // uniform over the CTA
-                if (active) {
-                    // REG_PF is even: the parity of tt is the parity of d, so the double buffer is indexed statically
-                    const double v = (d & 1) ? fma(a[d], car[il1], fma(b[d], car[iu1], c[d])) : fma(a[d], car[il0], fma(b[d], car[iu0], c[d]));
-                    if (d & 1) car[jw0] = v; else car[jw1] = v;
-                    a[d] = reg_ldg(pA + po); b[d] = reg_ldg(pB + po); c[d] = reg_ldg(pC + po);
-                    if (tt >= last0) reg_stg(pI + so, v);
-                }
-                if (++cpf == nsi) { cpf = 0; po = o0; } else po += stride;
-                if (++cnt == nsi) { cnt = 0; so = o0; } else so += stride;
-                __syncthreads();
-            }
-        }
+        for (int d = 0; d < REG_PF; d++) REG_STEP(d, t0 + d)
     }
+#pragma unroll
+    for (int d = 0; d < REG_PF; d++)
+        if (t0 + d < total) REG_STEP(d, t0 + d)   // uniform over the CTA
+#undef REG_STEP
     // periodic ghosts of the plane (:470-480): columns 0 / np-1 of the interior rows, then the two ghost rows.  The CTA
     // reads back its own stores; __syncthreads orders them.
     double* pl = Iout + base;
@@ -444,8 +451,9 @@ extern "C" int vrt_regular_formal_solve(int64_t nz, int64_t nx, int64_t ny, cons
                 k_reg_coef<<<grid, 256>>>(P, up, hz[idz], hz[izl], hz[izu], dcj.p, dcs.p, dS.p + pst * izl, dS.p + pst * izu,
                                           dA.p + pst * izl, dA.p + pst * izu, dS.p + pst * izc, dA.p + pst * izc, Iu, cA.p, cB.p, cC.p);
                 const int threads = ((P.np - 2 + 31) / 32) * 32;
-                if (threads <= 512) k_reg_rec<512><<<(unsigned)n_l, threads, sizeof(double) * 2 * P.np>>>(P, n_sweeps, cA.p, cB.p, cC.p, Ic);
-                else k_reg_rec<1024><<<(unsigned)n_l, threads, sizeof(double) * 2 * P.np>>>(P, n_sweeps, cA.p, cB.p, cC.p, Ic);
+                const size_t rec_smem = sizeof(double) * 2 * P.np;
+                if (threads <= 512) k_reg_rec<512><<<(unsigned)n_l, threads, rec_smem>>>(P, n_sweeps, cA.p, cB.p, cC.p, Ic);
+                else k_reg_rec<1024><<<(unsigned)n_l, threads, rec_smem>>>(P, n_sweeps, cA.p, cB.p, cC.p, Ic);
                 stats.kernels += 2;
                 stats.steps += (double)n_sweeps * (P.ns - 2);
             }
