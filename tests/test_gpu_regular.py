@@ -147,3 +147,17 @@ def test_workspace_release_and_reuse(oracle):
     ref = oracle.short_characteristics(z2, x2, y2, k, 0, S2[0], I02[0], alpha2[0])[0]
     assert np.array_equal(a, b) and close(c, ref)
     V.regular_release_workspace()
+
+
+def test_wide_rows_use_the_1024_thread_recurrence(oracle):
+    """rows wider than 514 points run the second instantiation of the recurrence kernel (prefetch depth 4)"""
+    import voronoirt_b200 as V
+    rng = np.random.default_rng(13)
+    z, x, y, S, alpha, I0 = random_box(rng, 5, 7, 603, 1)
+    for theta, phi in ((70.3, 346.4), (109.7, 193.6)):
+        down = int(theta < 90)
+        k = kvec(theta, phi)
+        ref, ref_branch = oracle.short_characteristics(z, x, y, k, down, S[0], I0[0], alpha[0])
+        I, branch = solve(V, z, x, y, k, down, S[0], I0[0], alpha[0])
+        assert np.array_equal(branch, ref_branch) and 2 in branch
+        assert close(I, ref)

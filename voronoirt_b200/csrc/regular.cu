@@ -24,8 +24,7 @@
 namespace vrt {
 namespace {
 
-constexpr int REG_PF = 8;   // coefficient rows in flight per thread in the recurrence (even: see k_reg_rec)
-static_assert(REG_PF % 2 == 0, "the carried-row double buffer is indexed by the parity of the unrolled step");
+constexpr int REG_PF = 12;   // coefficient rows in flight per thread in the recurrence (a third of it for rows wider than 514)
 
 struct RegPlane {
     int np, ns;          // extents of the j and s axes (ghost columns included)
@@ -210,10 +209,11 @@ __device__ __forceinline__ void reg_stg(double* p, double v) { asm volatile("st.
 // values reach HBM; its rows 1 and ns-2 are also written to the ghost rows ns-1 and 0 (:476-480).
 // The dependent chain of one row step is LDS, 2 FMA, STS, barrier; everything else (coefficient prefetch REG_PF rows
 // ahead, row counters) is off the chain.
-template <int MAXT>
+template <int MAXT, int PF>
 __global__ void __launch_bounds__(MAXT) k_reg_rec(RegPlane P, int n_sweeps, const double* __restrict__ cA,
                                                    const double* __restrict__ cB, const double* __restrict__ cC,
                                                    double* __restrict__ Iout) {
+    static_assert(PF % 2 == 0, "the carried-row double buffer is indexed by the parity of the unrolled step");
     extern __shared__ double car[];   // 2 x np carried rows
     const int np = P.np, ns = P.ns, nsi = P.ns - 2;
     // threads past the last interior column repeat it (same values to the same addresses) instead of idling behind a
@@ -235,15 +235,15 @@ __global__ void __launch_bounds__(MAXT) k_reg_rec(RegPlane P, int n_sweeps, cons
     int il1 = il + np, iu1 = iu + np, jw0 = j, jw1 = j + np, il0 = il, iu0 = iu;
     asm volatile("" : "+r"(il0), "+r"(iu0), "+r"(il1), "+r"(iu1), "+r"(jw0), "+r"(jw1));
     __syncthreads();
-    double a[REG_PF], b[REG_PF], c[REG_PF];
+    double a[PF], b[PF], c[PF];
     int po = o0, so = o0;   // rows being prefetched / solved; both wrap into the next sweep
 #pragma unroll
-    for (int d = 0; d < REG_PF; d++) {
+    for (int d = 0; d < PF; d++) {
         a[d] = reg_ldg(pA + po); b[d] = reg_ldg(pB + po); c[d] = reg_ldg(pC + po);
         po += stride;
         if (po == o_end) po = o0;
     }
-    // one row step; REG_PF is even, so the parity of tt is the parity of d and the double buffer is indexed statically
+    // one row step; PF is even, so the parity of tt is the parity of d and the double buffer is indexed statically
 #define REG_STEP(d, tt)                                                                                     \
     {                                                                                                       \
         const double v = ((d)&1) ? fma(a[d], car[il1], fma(b[d], car[iu1], c[d]))                           \
@@ -258,12 +258,12 @@ __global__ void __launch_bounds__(MAXT) k_reg_rec(RegPlane P, int n_sweeps, cons
         __syncthreads();                                                                                    \
     }
     int t0 = 0;
-    for (; t0 + REG_PF <= total; t0 += REG_PF) {
+    for (; t0 + PF <= total; t0 += PF) {
 #pragma unroll
-        for (int d = 0; d < REG_PF; d++) REG_STEP(d, t0 + d)
+        for (int d = 0; d < PF; d++) REG_STEP(d, t0 + d)
     }
 #pragma unroll
-    for (int d = 0; d < REG_PF; d++)
+    for (int d = 0; d < PF; d++)
         if (t0 + d < total) REG_STEP(d, t0 + d)   // uniform over the CTA
 #undef REG_STEP
     // periodic ghosts of the plane (:470-480): columns 0 / np-1 of the interior rows, then the two ghost rows.  The CTA
@@ -452,8 +452,8 @@ extern "C" int vrt_regular_formal_solve(int64_t nz, int64_t nx, int64_t ny, cons
                                           dA.p + pst * izl, dA.p + pst * izu, dS.p + pst * izc, dA.p + pst * izc, Iu, cA.p, cB.p, cC.p);
                 const int threads = ((P.np - 2 + 31) / 32) * 32;
                 const size_t rec_smem = sizeof(double) * 2 * P.np;
-                if (threads <= 512) k_reg_rec<512><<<(unsigned)n_l, threads, rec_smem>>>(P, n_sweeps, cA.p, cB.p, cC.p, Ic);
-                else k_reg_rec<1024><<<(unsigned)n_l, threads, rec_smem>>>(P, n_sweeps, cA.p, cB.p, cC.p, Ic);
+                if (threads <= 512) k_reg_rec<512, REG_PF><<<(unsigned)n_l, threads, rec_smem>>>(P, n_sweeps, cA.p, cB.p, cC.p, Ic);
+                else k_reg_rec<1024, REG_PF / 3><<<(unsigned)n_l, threads, rec_smem>>>(P, n_sweeps, cA.p, cB.p, cC.p, Ic);
                 stats.kernels += 2;
                 stats.steps += (double)n_sweeps * (P.ns - 2);
             }
