@@ -190,7 +190,25 @@ int vrt_regular_formal_solve(int64_t nz, int64_t nx, int64_t ny, const double* z
                              const double k[3], int32_t down, int32_t n_sweeps, int64_t nlam, const double* S,
                              const double* alpha, const double* I0, double* I_out, int32_t* plane_branch);
 
-/* vrt_regular_formal_solve keeps its device workspace (3-4 internal copies of one wavelength chunk) between calls;
+/* J_λ_regular for a direction-independent opacity (lambda_continuum.jl:1-24; the line form lambda_iteration.jl:23-55
+ * differs only in the per-direction alpha): J = Σ_i weights[i] * I_i over the quadrature, rays with θ > 90 solved upwards
+ * from I0_up at z[0], rays with θ < 90 downwards from I0_down at z[nz-1] (NULL = zero, as the reference has it); θ = 90
+ * belongs to neither branch.  S, alpha, J: nlam x nz x nx x ny; I0_up, I0_down: nlam x nx x ny.  S and alpha are laid out
+ * once per internal layout and reused by all directions. */
+int vrt_regular_mean_intensity(int64_t nz, int64_t nx, int64_t ny, const double* z, const double* x, const double* y,
+                               const vrt_quadrature* quad, int32_t n_sweeps, int64_t nlam, const double* S,
+                               const double* alpha, const double* I0_up, const double* I0_down, double* J);
+
+/* Λ_regular, 500 nm continuum (lambda_continuum.jl:58-107) with its criterion (:162-179, maximum over ε > 1e-4 only):
+ * S = B_0; while criterion: J = J_λ_regular(S_old); S_new = (1-ε)J + εB_0.  alpha, eps_l, B0: nz x nx x ny as the host
+ * computes them at :66-85 (Transparency.jl quantities stay on the host); the bottom boundary is B0[0,:,:] (:16).
+ * S_out, J_out (optional): nz x nx x ny.  cb as in vrt_lambda_iterate. */
+int vrt_regular_lambda_iterate(int64_t nz, int64_t nx, int64_t ny, const double* z, const double* x, const double* y,
+                               const vrt_quadrature* quad, int32_t n_sweeps, const double* alpha, const double* eps_l,
+                               const double* B0, double eps, int32_t maxiter, vrt_iter_cb cb, void* user, double* S_out,
+                               double* J_out, vrt_result* out);
+
+/* the regular-grid entries keep their device workspace (3-6 internal copies of one wavelength chunk) between calls;
  * this frees it, e.g. before handing the GPU to an irregular-grid solver. */
 int vrt_regular_release_workspace(void);
 

@@ -246,3 +246,30 @@ def short_characteristics(z, x, y, k, down, S, I_0, alpha, n_sweeps=3):
     lib().orc_short_characteristics(C.c_int64(nz), C.c_int64(nx), C.c_int64(ny), _p(z), _p(x), _p(y), _p(k), C.c_int(down),
                                     _p(S), _p(I_0), _p(alpha), C.c_int(n_sweeps), _p(out), _p(planes))
     return out, planes
+
+
+def J_regular(z, x, y, weights, theta, phi, S, alpha, I0_up, n_sweeps=3):
+    """lambda_continuum.jl:1-24 for one wavelength.  S, alpha (nz, nx, ny) Fortran-ordered; I0_up (nx, ny)."""
+    z, x, y, weights, theta, phi = map(f64, (z, x, y, weights, theta, phi))
+    S = np.asfortranarray(S, dtype=np.float64)
+    alpha = np.asfortranarray(alpha, dtype=np.float64)
+    I0_up = np.asfortranarray(I0_up, dtype=np.float64)
+    nz, nx, ny = S.shape
+    J = np.zeros((nz, nx, ny), order="F")
+    lib().orc_J_regular(C.c_int64(nz), C.c_int64(nx), C.c_int64(ny), _p(z), _p(x), _p(y), C.c_int64(len(weights)), _p(weights),
+                        _p(theta), _p(phi), C.c_int(n_sweeps), _p(S), _p(alpha), _p(I0_up), _p(J))
+    return J
+
+
+def lambda_regular(z, x, y, weights, theta, phi, alpha, eps_l, B0, eps=1e-3, maxiter=150, n_sweeps=3):
+    """lambda_continuum.jl:58-107 -> (J, S, convergence, iterations)"""
+    z, x, y, weights, theta, phi = map(f64, (z, x, y, weights, theta, phi))
+    alpha, eps_l, B0 = (np.asfortranarray(a, dtype=np.float64) for a in (alpha, eps_l, B0))
+    nz, nx, ny = B0.shape
+    S = np.zeros((nz, nx, ny), order="F")
+    J = np.zeros((nz, nx, ny), order="F")
+    conv = np.zeros(maxiter + 1)
+    it = lib().orc_lambda_regular(C.c_int64(nz), C.c_int64(nx), C.c_int64(ny), _p(z), _p(x), _p(y), C.c_int64(len(weights)),
+                                  _p(weights), _p(theta), _p(phi), C.c_int(n_sweeps), C.c_double(eps), C.c_int(maxiter),
+                                  _p(alpha), _p(eps_l), _p(B0), _p(S), _p(J), _p(conv))
+    return J, S, conv, it

@@ -22,6 +22,7 @@ typedef struct {
     const double *z, *x, *y;
 } reg_atmos;
 
+#define ORC_PI 3.14159265358979323846
 #define A3(a, iz, ix, iy) ((a)[((iz)-1) + at->nz * (((ix)-1) + at->nx * ((iy)-1))])
 #define P2(a, ix, iy) ((a)[((ix)-1) + at->nx * ((iy)-1)])
 
@@ -229,4 +230,62 @@ void orc_short_characteristics(int64_t nz, int64_t nx, int64_t ny, const double*
     }
     free(prev);
     free(cur);
+}
+
+/* J_λ_regular, continuum form (lambda_continuum.jl:1-24): J = Σ_i w_i I_i; θ > 90 up from I0_up at z[1], θ < 90 down
+ * from zero at z[end]; θ = 90 contributes nothing.  The source passes I_0 as a keyword to a positional parameter (Q12)
+ * and cannot run as shipped; this is the evident intent (the same as the Voronoi twin, lambda_continuum.jl:27-56). */
+void orc_J_regular(int64_t nz, int64_t nx, int64_t ny, const double* z, const double* x, const double* y, int64_t n_dirs,
+                   const double* weights, const double* theta, const double* phi, int n_sweeps, const double* S, const double* al,
+                   const double* I0_up, double* J) {
+    size_t vol = (size_t)(nz * nx * ny);
+    double* I = (double*)malloc(sizeof(double) * vol);
+    double* zero = (double*)calloc((size_t)(nx * ny), sizeof(double));
+    memset(J, 0, sizeof(double) * vol);
+    for (int64_t i = 0; i < n_dirs; i++) {
+        double th = theta[i], ph = phi[i];
+        double k[3] = {cos(th * ORC_PI / 180), cos(ph * ORC_PI / 180) * sin(th * ORC_PI / 180), sin(ph * ORC_PI / 180) * sin(th * ORC_PI / 180)};
+        if (th > 90) orc_short_characteristics(nz, nx, ny, z, x, y, k, 0, S, I0_up, al, n_sweeps, I, NULL);
+        else if (th < 90) orc_short_characteristics(nz, nx, ny, z, x, y, k, 1, S, zero, al, n_sweeps, I, NULL);
+        else continue;
+        for (size_t c = 0; c < vol; c++) J[c] += weights[i] * I[c];
+    }
+    free(I);
+    free(zero);
+}
+
+/* Λ_regular (lambda_continuum.jl:58-107) with criterion (:162-179): S = B_0; while max over thick (ε > 1e-4) of
+ * |1 - S_old/S_new| > ϵ and i < maxiter: J = J_λ_regular(S_old); S_new = (1-ε)J + εB_0.  conv[i] = criterion value
+ * evaluated before iteration i+1.  Returns the number of iterations. */
+int orc_lambda_regular(int64_t nz, int64_t nx, int64_t ny, const double* z, const double* x, const double* y, int64_t n_dirs,
+                       const double* weights, const double* theta, const double* phi, int n_sweeps, double eps, int maxiter,
+                       const double* al, const double* eps_l, const double* B0, double* S, double* J, double* conv) {
+    size_t vol = (size_t)(nz * nx * ny);
+    double* S_old = (double*)calloc(vol, sizeof(double));
+    double* I0 = (double*)malloc(sizeof(double) * (size_t)(nx * ny));
+    for (int64_t iy = 0; iy < ny; iy++)
+        for (int64_t ix = 0; ix < nx; ix++) I0[ix + nx * iy] = B0[0 + nz * (ix + nx * iy)];
+    memcpy(S, B0, sizeof(double) * vol);
+    memset(J, 0, sizeof(double) * vol);
+    int i = 0;
+    for (;;) {
+        double diff = 0;
+        int isnan_ = 0;
+        for (size_t c = 0; c < vol; c++)
+            if (eps_l[c] > 1e-4) {
+                double d = fabs(1 - S_old[c] / S[c]);
+                if (d != d) isnan_ = 1;
+                else if (d > diff) diff = d;
+            }
+        if (isnan_) diff = NAN;
+        conv[i] = diff;
+        if (!(diff > eps && i < maxiter)) break;
+        memcpy(S_old, S, sizeof(double) * vol);
+        orc_J_regular(nz, nx, ny, z, x, y, n_dirs, weights, theta, phi, n_sweeps, S_old, al, I0, J);
+        for (size_t c = 0; c < vol; c++) S[c] = (1 - eps_l[c]) * J[c] + eps_l[c] * B0[c];
+        i++;
+    }
+    free(S_old);
+    free(I0);
+    return i;
 }

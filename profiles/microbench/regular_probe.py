@@ -73,6 +73,29 @@ for theta, phi in DIRS:
                  "gpu_updates_per_s": upd / (wall * 1e-3), "cpu_1thread_s_per_lam": cpu_s,
                  "cpu_updates_per_s": upd / nlam / cpu_s})
     print(json.dumps(rows[-1]), flush=True)
+if os.environ.get('VRT_PROBE_J'):
+    # J_λ_regular over all ul7n12 directions (BASELINE metric on the config-4 shape), everything resident in HBM
+    quad = np.loadtxt(os.path.join(ROOT, "voronoirt_b200", "quadratures", "ul7n12.dat"))
+    w, t, p = (np.ascontiguousarray(quad[:, i]) for i in range(3))
+    from voronoirt_b200 import _abi
+    q = _abi.vrt_quadrature(len(w), w.ctypes.data, t.ctypes.data, p.ctypes.data)
+    Jt = torch.empty_like(S)
+    best = None
+    import ctypes
+    for rep in range(3):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        _lib.check(L.vrt_regular_mean_intensity(nz, nx, ny, _ptr(z), _ptr(x), _ptr(y), ctypes.byref(q), 3, nlam, _ptr(S), _ptr(alpha),
+                                                _ptr(I0), None, _ptr(Jt)))
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        st = _lib.last_stats()
+        best = (dt, st) if best is None or dt < best[0] else best
+    upd = (nz - 1) * (nx - 2) * (ny - 2) * nlam * len(w)
+    rec = {"what": "J_lambda_regular, ul7n12, %d wavelengths, 400x258x258" % nlam, "wall_ms": best[0] * 1e3, "plane_loops_ms": best[1]["sweep_ms"],
+           "launches": best[1]["kernels"], "updates_per_s": upd / best[0], "J_mean": float(Jt.mean())}
+    print(json.dumps(rec), flush=True)
+    rows.append(rec)
 if rows:
     json.dump(rows, open(os.path.join(ROOT, "gpurun_out", "regular_probe_%d.json" % nlam), "w"), indent=1)
 V.regular_release_workspace()

@@ -161,3 +161,63 @@ def test_wide_rows_use_the_1024_thread_recurrence(oracle):
         I, branch = solve(V, z, x, y, k, down, S[0], I0[0], alpha[0])
         assert np.array_equal(branch, ref_branch) and 2 in branch
         assert close(I, ref)
+
+
+def continuum_box(rng, nz, nx, ny):
+    """periodic alpha, eps, B0 for the regular continuum Λ-iteration (lambda_continuum.jl:58-107)"""
+    z = np.cumsum(rng.uniform(0.3, 2.0, nz))
+    x = (np.arange(nx) - 1) * 1.1
+    y = (np.arange(ny) - 1) * 0.9
+    alpha = np.asfortranarray(10.0 ** rng.uniform(-2, 1, (nz, nx, ny)))
+    eps_l = np.asfortranarray(10.0 ** rng.uniform(-5, 0, (nz, nx, ny)))      # both sides of the `thick` threshold 1e-4
+    B0 = np.asfortranarray(rng.uniform(1.0, 2.0, (nz, nx, ny)))
+    for a in (alpha, eps_l, B0):
+        a[:, 0, :] = a[:, -2, :]; a[:, -1, :] = a[:, 1, :]
+        a[:, :, 0] = a[:, :, -2]; a[:, :, -1] = a[:, :, 1]
+    return z, x, y, alpha, eps_l, B0
+
+
+def test_J_regular_vs_oracle_and_batched(oracle, monkeypatch):
+    import voronoirt_b200 as V
+    rng = np.random.default_rng(21)
+    nlam = 3
+    z, x, y, S, alpha, I0 = random_box(rng, 9, 13, 16, nlam)
+    atm = V.Atmosphere(z, x, y)
+    quad = (QUAD[:, 0], QUAD[:, 1], QUAD[:, 2])
+    ref = np.stack([oracle.J_regular(z, x, y, *quad, S[l], alpha[l], I0[l]) for l in range(nlam)])
+    J = V.J_λ_regular(S, alpha, atm, quad, I_0=I0)
+    assert close(J, ref), np.abs(J - ref).max()
+    J1 = V.J_λ_regular(S[1], alpha[1], atm, quad, I_0=I0[1])                 # one wavelength, 3-D arrays
+    assert np.array_equal(J1, J[1])
+    monkeypatch.setenv("VRT_REG_LAM_CHUNK", "2")
+    J2 = V.J_λ_regular(S, alpha, atm, quad, I_0=I0)
+    monkeypatch.delenv("VRT_REG_LAM_CHUNK")
+    assert np.array_equal(J, J2)
+    # J is the weighted sum of the single-direction solutions of the formal solver
+    acc = np.zeros_like(S[0])
+    for w, theta, phi in QUAD:
+        down = int(theta < 90)
+        bnd = np.zeros_like(I0[0]) if down else I0[0]
+        acc += w * solve(V, z, x, y, kvec(theta, phi), down, S[0], bnd, alpha[0])[0]
+    assert np.abs(acc - J[0]).max() <= 1e-13 * np.abs(J[0]).max()
+    V.regular_release_workspace()
+
+
+def test_lambda_regular_vs_oracle(oracle):
+    import voronoirt_b200 as V
+    rng = np.random.default_rng(22)
+    z, x, y, alpha, eps_l, B0 = continuum_box(rng, 8, 11, 12)
+    quad = (QUAD[:, 0], QUAD[:, 1], QUAD[:, 2])
+    Jr, Sr, conv, it = oracle.lambda_regular(z, x, y, *quad, alpha, eps_l, B0, eps=1e-4, maxiter=60)
+    seen = []
+    J, S, a = V.Λ_regular(1e-4, 60, V.Atmosphere(z, x, y), quad, alpha, eps_l, B0, callback=lambda rec: seen.append(rec["diff"]))
+    res = V.Λ_regular.last
+    assert res["iterations"] == it and res["converged"] and 0 < it < 60
+    assert close(S, Sr) and close(J, Jr)
+    assert np.allclose(seen, conv[:it], rtol=1e-9) and abs(res["diff"] - conv[it]) <= 1e-9 * conv[it]
+    # maxiter reached: not converged, same state as the oracle after 3 iterations
+    Jr3, Sr3, conv3, it3 = oracle.lambda_regular(z, x, y, *quad, alpha, eps_l, B0, eps=1e-12, maxiter=3)
+    J3, S3, _ = V.Λ_regular(1e-12, 3, V.Atmosphere(z, x, y), quad, alpha, eps_l, B0)
+    assert V.Λ_regular.last["iterations"] == it3 == 3 and not V.Λ_regular.last["converged"]
+    assert close(S3, Sr3) and close(J3, Jr3)
+    V.regular_release_workspace()

@@ -79,3 +79,24 @@ def test_oracle_regular_thick_limit(oracle):
         I, _ = oracle.short_characteristics(ax, ax, ax, kvec(theta, phi), down, S, I0, alpha)
         inner = I[:-1] if down else I[1:]
         assert np.abs(inner - 3.5).max() < 1e-12
+
+
+def test_oracle_J_regular_is_the_weighted_sum_and_lambda_converges(oracle):
+    """lambda_continuum.jl:1-24, :58-107: J = Σ w_i I_i (up from I_0, down from zero); with ε = 1 the source function
+    stays B_0 and the loop stops after one iteration with criterion 0."""
+    rng = np.random.default_rng(4)
+    n = 8
+    ax = np.linspace(0.0, 1.0, n)
+    quad = np.loadtxt(os.path.join(HERE, "..", "voronoirt_b200", "quadratures", "ul7n12.dat"))
+    S = np.asfortranarray(rng.uniform(0.5, 1.5, (n, n, n)))
+    al = np.asfortranarray(rng.uniform(0.5, 5.0, (n, n, n)))
+    I0 = np.asfortranarray(rng.uniform(0.0, 1.0, (n, n)))
+    J = oracle.J_regular(ax, ax, ax, quad[:, 0], quad[:, 1], quad[:, 2], S, al, I0)
+    acc = np.zeros_like(S)
+    for w, theta, phi in quad:
+        down = int(theta < 90)
+        acc += w * oracle.short_characteristics(ax, ax, ax, kvec(theta, phi), down, S, np.zeros_like(I0) if down else I0, al)[0]
+    assert np.abs(acc - J).max() <= 1e-15
+    ones = np.ones((n, n, n), order="F")
+    Jc, Sc, conv, it = oracle.lambda_regular(ax, ax, ax, quad[:, 0], quad[:, 1], quad[:, 2], al, ones, S, eps=1e-3, maxiter=10)
+    assert it == 1 and conv[0] == 1.0 and conv[1] == 0.0 and np.array_equal(Sc, S)

@@ -493,6 +493,65 @@ def Λ_voronoi(ϵ, maxiter, sites, *args, **kw):
     return J, S, _f(kw["α_cont"])
 
 
+def J_λ_regular(S_λ, α_cont, atmos, quadrature, I_0=None, I_0_down=None, n_sweeps=3):
+    """src/lambda_continuum.jl:1-24 (and lambda_iteration.jl:23-55 for a direction-independent α).  S_λ, α_cont:
+    (nz, nx, ny) or (nλ, nz, nx, ny); I_0: the bottom boundary the reference builds at :16, blackbody_λ(500 nm,
+    T[1,:,:]), (nx, ny) or (nλ, nx, ny); rays with θ < 90 start from zero (:19) unless I_0_down is given."""
+    nz, nx, ny = len(atmos.z), len(atmos.x), len(atmos.y)
+    S_λ, α_cont = _f(S_λ), _f(α_cont)
+    nlam = 1 if S_λ.ndim == 3 else S_λ.shape[0]
+    want = (nz, nx, ny) if S_λ.ndim == 3 else (nlam, nz, nx, ny)
+    if S_λ.shape != want or α_cont.shape != want:
+        raise ValueError("S_λ, α_cont must be (nz, nx, ny) or (nλ, nz, nx, ny)")
+    bshape = want[:-3] + (nx, ny)
+    up = None if I_0 is None else _f(I_0)
+    dn = None if I_0_down is None else _f(I_0_down)
+    for b in (up, dn):
+        if b is not None and b.shape != bshape:
+            raise ValueError("I_0 must be %s" % (bshape,))
+    if up is None:
+        up = np.zeros(bshape, order="F")
+    q = _as_quadrature(quadrature)
+    J = np.zeros_like(S_λ, order="F")
+    check(lib().vrt_regular_mean_intensity(nz, nx, ny, _ptr(atmos.z), _ptr(atmos.x), _ptr(atmos.y), C.byref(q), int(n_sweeps), nlam,
+                                           _ptr(S_λ), _ptr(α_cont), _ptr(up), _ptr(dn), _ptr(J)))
+    return J
+
+
+def Λ_regular(ϵ, maxiter, atmos, quadrature, α_cont, ε_λ, B_0, n_sweeps=3, callback=None):
+    """src/lambda_continuum.jl:58-107 -> (J, S, α_cont).  α_cont, ε_λ, B_0 (nz, nx, ny) are what the reference computes with
+    Transparency.jl at :66-85 before its loop."""
+    nz, nx, ny = len(atmos.z), len(atmos.x), len(atmos.y)
+    α_cont, ε_λ, B_0 = _f(α_cont), _f(ε_λ), _f(B_0)
+    for a in (α_cont, ε_λ, B_0):
+        if a.shape != (nz, nx, ny):
+            raise ValueError("α_cont, ε_λ, B_0 must be (nz, nx, ny)")
+    q = _as_quadrature(quadrature)
+    S = np.zeros((nz, nx, ny), order="F")
+    J = np.zeros((nz, nx, ny), order="F")
+    res = _abi.vrt_result()
+    history = []
+
+    def tramp(info, user):
+        i = info.contents
+        rec = {f: getattr(i, f) for f, _ in _abi.vrt_iter_info._fields_ if f != "reserved0"}
+        history.append(rec)
+        try:
+            return int(callback(rec) or 0) if callback else 0
+        except Exception as ex:
+            print("iteration callback failed:", ex)
+            return 1
+    cb = _abi.vrt_iter_cb(tramp)
+    check(lib().vrt_regular_lambda_iterate(nz, nx, ny, _ptr(atmos.z), _ptr(atmos.x), _ptr(atmos.y), C.byref(q), int(n_sweeps),
+                                           _ptr(α_cont), _ptr(ε_λ), _ptr(B_0), float(ϵ), int(maxiter), cb, None, _ptr(S), _ptr(J),
+                                           C.byref(res)))
+    Λ_regular.last = {"iterations": res.iterations, "converged": bool(res.converged), "diff": res.diff, "seconds": res.seconds,
+                      "history": history}
+    return J, S, α_cont
+
+
 # ASCII aliases
 J_lambda_voronoi = J_λ_voronoi
 Lambda_voronoi = Λ_voronoi
+J_lambda_regular = J_λ_regular
+Lambda_regular = Λ_regular

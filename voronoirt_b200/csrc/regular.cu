@@ -18,6 +18,8 @@
 // because r_x and r_y do not depend on the plane.  Two tiled transposes convert in and out.
 #include <algorithm>
 #include <math.h>
+#include <string.h>
+#include <chrono>
 #include <mutex>
 #include "vrt_internal.h"
 
@@ -65,9 +67,10 @@ __device__ __forceinline__ double reg_bilinear(double xm, double ym, double x1, 
 // ------------------------------------------------------------------ layout conversion
 // src: caller's (nlam_src, nz, nx, ny) column-major, wavelengths [l0, l0+lc) -> dst [iz][l][s][j].
 // Tile of 32 (q = l + lc*iz) x 32 (j) per block, one s per blockIdx.z; TO_INTERNAL = 0 is the inverse copy.
+// For the inverse copy the result is w * value, added to what dst holds when `accumulate` (J += weights[i] * I).
 template <int TO_INTERNAL>
 __global__ void k_reg_transpose(const double* __restrict__ src, double* __restrict__ dst, int64_t nlam_src, int64_t l0,
-                                int lc, int64_t nz, int64_t nx, int64_t ny, int par_is_x) {
+                                int lc, int64_t nz, int64_t nx, int64_t ny, int par_is_x, double w, int accumulate) {
     __shared__ double tile[32][33];
     const int np = par_is_x ? (int)nx : (int)ny, ns = par_is_x ? (int)ny : (int)nx;
     const int64_t Q = (int64_t)lc * nz;
@@ -107,7 +110,11 @@ __global__ void k_reg_transpose(const double* __restrict__ src, double* __restri
         for (int r = 0; r < 4; r++) {
             const int j = j0 + ty + 8 * r;
             const int64_t q = q0 + tx;
-            if (j < np && q < Q) dst[user_off(q, j)] = tile[tx][ty + 8 * r];
+            if (j < np && q < Q) {
+                const int64_t o = user_off(q, j);
+                const double v = w * tile[tx][ty + 8 * r];
+                dst[o] = accumulate ? dst[o] + v : v;
+            }
         }
     }
 }
@@ -281,23 +288,353 @@ __global__ void __launch_bounds__(MAXT) k_reg_rec(RegPlane P, int n_sweeps, cons
     }
 }
 
-// Device workspace of vrt_regular_formal_solve, kept between calls (a Λ-iteration calls it n_directions times per
+// Device workspace of the regular-grid entries, kept between calls (a Λ-iteration solves n_directions times per
 // iteration with the same shapes; cudaMalloc/cudaFree of tens of GB cost more than the solve).  Grow-only; released by
-// vrt_regular_release_workspace().
+// vrt_regular_release_workspace().  S and alpha are held once per internal layout (j = x and j = y).
 struct RegWorkspace {
     int device = -1;
-    DevBuf<double> dS, dA, dI, stage, stage0, cA, cB, cC, dcj, dcs;
-    size_t bytes() const { return 8 * (dS.n + dA.n + dI.n + stage.n + stage0.n + cA.n + cB.n + cC.n + dcj.n + dcs.n); }
+    DevBuf<double> dS[2], dA[2], dI, stage, stage0, cA, cB, cC, dx, dy, dJ;
+    DevBuf<unsigned long long> diff_bits;
+    DevBuf<int> diff_nan;
+    size_t bytes() const {
+        return 8 * (dS[0].n + dS[1].n + dA[0].n + dA[1].n + dI.n + stage.n + stage0.n + cA.n + cB.n + cC.n + dx.n + dy.n + dJ.n);
+    }
     void release() {
-        dS.release(); dA.release(); dI.release(); stage.release(); stage0.release();
-        cA.release(); cB.release(); cC.release(); dcj.release(); dcs.release();
+        for (int i = 0; i < 2; i++) { dS[i].release(); dA[i].release(); }
+        dI.release(); stage.release(); stage0.release(); cA.release(); cB.release(); cC.release();
+        dx.release(); dy.release(); dJ.release(); diff_bits.release(); diff_nan.release();
     }
 };
 std::mutex g_reg_mu;
 RegWorkspace* g_reg_ws = nullptr;   // never destroyed at exit: the CUDA runtime may already be gone by then
 
-inline int host_copy(double* dst, const double* src, int64_t n) {
-    VRT_CUDA(cudaMemcpy(dst, src, sizeof(double) * (size_t)n, cudaMemcpyDefault));
+struct RegGeom {
+    int64_t nz = 0, nx = 0, ny = 0;
+    size_t plane = 0, vol = 0;
+    std::vector<double> hz, hx, hy;
+};
+
+struct RegDir {
+    RegPlane P;
+    double k[3];
+    int down;
+    double r_x, r_y;
+};
+
+int reg_check_geom(const char* who, int64_t nz, int64_t nx, int64_t ny, const double* z, const double* x, const double* y, RegGeom* G) {
+    if (!z || !x || !y || nz < 2 || nx < 3 || ny < 3) {
+        set_error("%s: bad grid arguments", who);
+        return VRT_E_INVALID;
+    }
+    if (nx > 1026 || ny > 1026) {
+        set_error("%s: nx, ny <= 1026 (one thread per interior point of a row in the recurrence)", who);
+        return VRT_E_INVALID;
+    }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        set_error("%s: no CUDA device (this library has no CPU path)", who);
+        return VRT_E_CUDA;
+    }
+    G->nz = nz; G->nx = nx; G->ny = ny;
+    G->plane = (size_t)nx * ny;
+    G->vol = G->plane * nz;
+    G->hz.resize(nz); G->hx.resize(nx); G->hy.resize(ny);
+    VRT_CUDA(cudaMemcpy(G->hz.data(), z, sizeof(double) * nz, cudaMemcpyDefault));
+    VRT_CUDA(cudaMemcpy(G->hx.data(), x, sizeof(double) * nx, cudaMemcpyDefault));
+    VRT_CUDA(cudaMemcpy(G->hy.data(), y, sizeof(double) * ny, cudaMemcpyDefault));
+    return VRT_OK;
+}
+
+// characteristics.jl:34-40: path lengths to the x and y faces, xy_intersect signs, and the internal layout they imply
+int reg_dir_setup(const char* who, const RegGeom& G, const double k[3], int down, RegDir* D) {
+    if (!(k[0] == k[0]) || !(k[1] == k[1]) || !(k[2] == k[2]) || k[0] == 0.0) {
+        set_error("%s: direction must be finite with k[0] != 0", who);
+        return VRT_E_INVALID;
+    }
+    const double dx = G.hx[1] - G.hx[0], dy = G.hy[1] - G.hy[0];
+    D->r_x = fabs(dx / k[1]);
+    D->r_y = fabs(dy / k[2]);
+    int sx = 1, sy = 1;
+    if (k[1] > 0 && k[2] > 0) { sx = -1; sy = -1; }
+    else if (k[1] < 0 && k[2] > 0) { sx = 1; sy = -1; }
+    else if (k[1] < 0 && k[2] < 0) { sx = 1; sy = 1; }
+    else if (k[1] > 0 && k[2] < 0) { sx = -1; sy = 1; }
+    // argmin([r_z, r_x, r_y]) takes the first minimum: a sideways plane is xz only when r_y < r_x strictly
+    RegPlane& P = D->P;
+    P.par_is_x = (D->r_y < D->r_x) ? 1 : 0;
+    P.np = (int)(P.par_is_x ? G.nx : G.ny);
+    P.ns = (int)(P.par_is_x ? G.ny : G.nx);
+    P.sgn_j = P.par_is_x ? sx : sy;
+    P.sgn_s = P.par_is_x ? sy : sx;
+    P.kz = k[0];
+    P.kj = P.par_is_x ? k[1] : k[2];
+    P.ks = P.par_is_x ? k[2] : k[1];
+    P.lc = 0;
+    D->k[0] = k[0]; D->k[1] = k[1]; D->k[2] = k[2];
+    D->down = down ? 1 : 0;
+    return VRT_OK;
+}
+
+int reg_workspace(RegWorkspace** out) {
+    if (!g_reg_ws) g_reg_ws = new RegWorkspace();
+    RegWorkspace& W = *g_reg_ws;
+    int cur_dev = 0;
+    VRT_CUDA(cudaGetDevice(&cur_dev));
+    if (W.device != cur_dev) { W.release(); W.device = cur_dev; }
+    *out = &W;
+    return VRT_OK;
+}
+
+// wavelengths per chunk when `vols` internal volumes and `planes` planes are needed per wavelength
+int reg_plan_chunk(const char* who, const RegGeom& G, const RegWorkspace& W, int64_t nlam, double vols, double planes, int64_t* lc_out) {
+    size_t free_b = 0, total_b = 0;
+    VRT_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    free_b += W.bytes();   // what the workspace already holds is ours to reuse
+    const double per_lam = 8.0 * (vols * G.vol + planes * G.plane);
+    int64_t lc = (int64_t)std::min<double>((double)nlam, floor(0.9 * (double)free_b / per_lam));
+    if (const char* e = getenv("VRT_REG_LAM_CHUNK")) lc = std::max<int64_t>(1, std::min<int64_t>(lc, atoll(e)));
+    if (lc < 1) {
+        set_error("%s: one wavelength of a %lld x %lld x %lld grid needs %.1f GB, %.1f GB free", who, (long long)G.nz,
+                  (long long)G.nx, (long long)G.ny, per_lam / 1e9, free_b / 1e9);
+        return VRT_E_NOMEM;
+    }
+    *lc_out = std::min<int64_t>(lc, 65535);
+    return VRT_OK;
+}
+
+int reg_common_buffers(const RegGeom& G, RegWorkspace& W, int64_t lc) {
+    const size_t need_pl = G.plane * lc;
+    VRT_TRY(W.cA.ensure(need_pl)); VRT_TRY(W.cB.ensure(need_pl)); VRT_TRY(W.cC.ensure(need_pl));
+    VRT_TRY(W.dx.ensure(G.nx)); VRT_TRY(W.dy.ensure(G.ny));
+    VRT_CUDA(cudaMemcpy(W.dx.p, G.hx.data(), sizeof(double) * G.nx, cudaMemcpyHostToDevice));
+    VRT_CUDA(cudaMemcpy(W.dy.p, G.hy.data(), sizeof(double) * G.ny, cudaMemcpyHostToDevice));
+    return VRT_OK;
+}
+
+// user array (host or device; nlam wavelengths, nz_ planes) -> internal layout of wavelengths [l0, l0+n_l)
+int reg_load(const RegGeom& G, const double* src, bool on_dev, int64_t nz_, int64_t nlam, int64_t l0, int64_t n_l, int par_is_x,
+             double* dst, DevBuf<double>& stg, SweepStats* st) {
+    const double* s_dev = src;
+    int64_t ld = nlam, lo = l0;
+    const size_t rows = (size_t)nz_ * G.plane;
+    if (!on_dev) {
+        VRT_TRY(stg.ensure(rows * n_l));
+        if (n_l == nlam) VRT_CUDA(cudaMemcpy(stg.p, src, sizeof(double) * rows * nlam, cudaMemcpyHostToDevice));
+        else VRT_CUDA(cudaMemcpy2D(stg.p, sizeof(double) * n_l, src + l0, sizeof(double) * nlam, sizeof(double) * n_l, rows, cudaMemcpyHostToDevice));
+        s_dev = stg.p; ld = n_l; lo = 0;
+    }
+    const int np = (int)(par_is_x ? G.nx : G.ny), ns = (int)(par_is_x ? G.ny : G.nx);
+    const dim3 grid((unsigned)((n_l * nz_ + 31) / 32), (unsigned)((np + 31) / 32), (unsigned)ns);
+    k_reg_transpose<1><<<grid, dim3(32, 8)>>>(s_dev, dst, ld, lo, (int)n_l, nz_, G.nx, G.ny, par_is_x, 1.0, 0);
+    VRT_CUDA(cudaGetLastError());
+    if (!on_dev) VRT_CUDA(cudaDeviceSynchronize());   // `stg` may be reused by the next load
+    st->kernels += 1;
+    return VRT_OK;
+}
+
+// internal layout -> user array (host or device): dst = w * I, or dst += w * I
+int reg_store(const RegGeom& G, const double* dI, double* dst, bool on_dev, int64_t nlam, int64_t l0, int64_t n_l, int par_is_x,
+              double w, int accumulate, DevBuf<double>& stg, SweepStats* st) {
+    double* d_dst = dst;
+    int64_t ld = nlam, lo = l0;
+    if (!on_dev) {
+        if (accumulate) {
+            set_error("internal: accumulating store needs a device destination");
+            return VRT_E_STATE;
+        }
+        VRT_TRY(stg.ensure(G.vol * n_l));
+        d_dst = stg.p; ld = n_l; lo = 0;
+    }
+    const int np = (int)(par_is_x ? G.nx : G.ny), ns = (int)(par_is_x ? G.ny : G.nx);
+    const dim3 grid((unsigned)((n_l * G.nz + 31) / 32), (unsigned)((np + 31) / 32), (unsigned)ns);
+    k_reg_transpose<0><<<grid, dim3(32, 8)>>>(dI, d_dst, ld, lo, (int)n_l, G.nz, G.nx, G.ny, par_is_x, w, accumulate);
+    VRT_CUDA(cudaGetLastError());
+    st->kernels += 1;
+    if (!on_dev) {
+        if (n_l == nlam) VRT_CUDA(cudaMemcpy(dst, stg.p, sizeof(double) * G.vol * nlam, cudaMemcpyDeviceToHost));
+        else VRT_CUDA(cudaMemcpy2D(dst + l0, sizeof(double) * nlam, stg.p, sizeof(double) * n_l, sizeof(double) * n_l, G.vol, cudaMemcpyDeviceToHost));
+    }
+    return VRT_OK;
+}
+
+// The walk over the planes (characteristics.jl:47-92 / :135-177).  dS, dA: internal S and alpha of this chunk in the
+// layout of D; dI: internal I with the boundary plane already in place.  branch (optional, host, nz) gets the routine per plane.
+int reg_plane_loop(const RegGeom& G, RegWorkspace& W, RegDir D, int n_sweeps, int64_t n_l, const double* dS, const double* dA,
+                   double* dI, SweepStats* st, int32_t* branch) {
+    RegPlane& P = D.P;
+    P.lc = (int)n_l;
+    const size_t pst = G.plane * n_l;   // plane stride of the internal arrays
+    const double* dcj = P.par_is_x ? W.dx.p : W.dy.p;
+    const double* dcs = P.par_is_x ? W.dy.p : W.dx.p;
+    const int64_t nz = G.nz;
+    const std::vector<double>& hz = G.hz;
+    if (branch) branch[D.down ? nz - 1 : 0] = 0;
+    for (int64_t step = 1; step < nz; step++) {
+        const int64_t idz = D.down ? nz - 1 - step : step;      // 0-based plane being solved
+        const int64_t idu = D.down ? idz + 1 : idz - 1;         // upwind plane
+        const double dz = D.down ? hz[idz + 1] - hz[idz] : hz[idz] - hz[idz - 1];
+        const double r_z = fabs(dz / D.k[0]);
+        int cut = 1;
+        double best = r_z;
+        if (D.r_x < best) { best = D.r_x; cut = 2; }
+        if (D.r_y < best) { best = D.r_y; cut = 3; }
+        if (branch) branch[idz] = cut;
+        double* Ic = dI + pst * idz;
+        const double* Iu = dI + pst * idu;
+        if (cut == 1) {
+            const dim3 grid((unsigned)((P.np * P.ns + 255) / 256), (unsigned)n_l);
+            k_reg_xy<<<grid, 256>>>(P, hz[idu] - hz[idz], dcj, dcs, dS + pst * idz, dA + pst * idz, dS + pst * idu, dA + pst * idu, Iu, Ic);
+            st->kernels += 1;
+        } else {
+            const int up = D.down ? 0 : 1;
+            const int64_t izl = up ? idz - 1 : idz, izu = izl + 1;
+            const int64_t izc = P.par_is_x ? izu : idz;          // Q13: xz takes the centre from the upper plane
+            const dim3 grid((unsigned)((P.np * P.ns + 255) / 256), (unsigned)n_l);
+            k_reg_coef<<<grid, 256>>>(P, up, hz[idz], hz[izl], hz[izu], dcj, dcs, dS + pst * izl, dS + pst * izu, dA + pst * izl,
+                                      dA + pst * izu, dS + pst * izc, dA + pst * izc, Iu, W.cA.p, W.cB.p, W.cC.p);
+            const int threads = ((P.np - 2 + 31) / 32) * 32;
+            const size_t rec_smem = sizeof(double) * 2 * P.np;
+            if (threads <= 512) k_reg_rec<512, REG_PF><<<(unsigned)n_l, threads, rec_smem>>>(P, n_sweeps, W.cA.p, W.cB.p, W.cC.p, Ic);
+            else k_reg_rec<1024, REG_PF / 3><<<(unsigned)n_l, threads, rec_smem>>>(P, n_sweeps, W.cA.p, W.cB.p, W.cC.p, Ic);
+            st->kernels += 2;
+            st->steps += (double)n_sweeps * (P.ns - 2);
+        }
+        VRT_CUDA(cudaGetLastError());
+    }
+    return VRT_OK;
+}
+
+struct EvPair {
+    cudaEvent_t a = nullptr, b = nullptr;
+    int create() {
+        VRT_CUDA(cudaEventCreate(&a));
+        VRT_CUDA(cudaEventCreate(&b));
+        return VRT_OK;
+    }
+    ~EvPair() {
+        if (a) cudaEventDestroy(a);
+        if (b) cudaEventDestroy(b);
+    }
+};
+
+// I0 plane of one chunk: a user array (nlam x nx x ny), or zero when NULL
+int reg_boundary(const RegGeom& G, RegWorkspace& W, const double* I0, int64_t nlam, int64_t l0, int64_t n_l, int par_is_x, int down,
+                 SweepStats* st) {
+    double* pl = W.dI.p + G.plane * n_l * (down ? G.nz - 1 : 0);
+    if (!I0) {
+        VRT_CUDA(cudaMemsetAsync(pl, 0, sizeof(double) * G.plane * n_l));
+        return VRT_OK;
+    }
+    return reg_load(G, I0, is_device_ptr(I0), 1, nlam, l0, n_l, par_is_x, pl, W.stage0, st);
+}
+
+// J_λ_regular (lambda_continuum.jl:1-24; lambda_iteration.jl:23-55 with a direction-independent alpha): J = Σ w_i I_i over
+// the quadrature, up rays (θ > 90) starting from I0_up at z[0], down rays (θ < 90) from I0_down (zero when NULL) at
+// z[nz-1].  S, alpha, J: device or host; when `alpha_ready` is given, the internal copies of alpha are kept across calls
+// (alpha_ready[layout] says which are valid) — the Λ-iteration's alpha does not change.  Caller holds g_reg_mu.
+int reg_mean_intensity(const char* who, const RegGeom& G, RegWorkspace& W, const vrt_quadrature* q, int n_sweeps, int64_t nlam,
+                       const double* S, const double* alpha, const double* I0_up, const double* I0_down, double* J,
+                       bool* alpha_ready, SweepStats* st) {
+    const bool dev_S = is_device_ptr(S), dev_a = is_device_ptr(alpha), dev_J = is_device_ptr(J);
+    const bool need_stage = !(dev_S && dev_a);
+    int64_t lc = 0;
+    VRT_TRY(reg_plan_chunk(who, G, W, nlam, 5.0 + (need_stage ? 1.0 : 0.0) + (dev_J ? 0.0 : 1.0), 4.0, &lc));
+    if (alpha_ready && lc < nlam) alpha_ready = nullptr;   // chunked: alpha is re-laid out per chunk
+    {
+        const size_t need_vol = G.vol * lc;
+        bool grow = W.dI.n < need_vol || (need_stage && W.stage.n < need_vol) || (!dev_J && W.dJ.n < need_vol);
+        for (int i = 0; i < 2; i++) grow = grow || (W.dS[i].p && W.dS[i].n < need_vol) || (W.dA[i].p && W.dA[i].n < need_vol);
+        if (grow) {
+            W.release();
+            if (alpha_ready) alpha_ready[0] = alpha_ready[1] = false;
+        }
+        VRT_TRY(W.dI.ensure(need_vol));
+        if (!dev_J) VRT_TRY(W.dJ.ensure(need_vol));
+        VRT_TRY(reg_common_buffers(G, W, lc));
+    }
+    EvPair ev;
+    VRT_TRY(ev.create());
+    for (int64_t l0 = 0; l0 < nlam; l0 += lc) {
+        const int64_t n_l = std::min<int64_t>(lc, nlam - l0);
+        bool have_S[2] = {false, false}, have_a_local[2] = {false, false};
+        bool* have_a = alpha_ready ? alpha_ready : have_a_local;
+        // J of this chunk accumulates on the device: in the caller's array, or in dJ (chunk-contiguous) for a host J
+        double* Jd = dev_J ? J : W.dJ.p;
+        const int64_t J_ld = dev_J ? nlam : n_l, J_l0 = dev_J ? l0 : 0;
+        int n_acc = 0;
+        for (int64_t i = 0; i < q->n_dirs; i++) {
+            const double th = q->theta[i], ph = q->phi[i];
+            if (!(th > 90) && !(th < 90)) continue;   // lambda_continuum.jl:15-21: θ = 90 belongs to neither branch
+            const int down = th < 90 ? 1 : 0;
+            const double k[3] = {cos(th * M_PI / 180), cos(ph * M_PI / 180) * sin(th * M_PI / 180), sin(ph * M_PI / 180) * sin(th * M_PI / 180)};
+            RegDir D;
+            VRT_TRY(reg_dir_setup(who, G, k, down, &D));
+            const int lay = D.P.par_is_x;
+            if (!have_S[lay]) {
+                VRT_TRY(W.dS[lay].ensure(G.vol * lc));
+                VRT_TRY(reg_load(G, S, dev_S, G.nz, nlam, l0, n_l, lay, W.dS[lay].p, W.stage, st));
+                have_S[lay] = true;
+            }
+            if (!have_a[lay]) {
+                VRT_TRY(W.dA[lay].ensure(G.vol * lc));
+                VRT_TRY(reg_load(G, alpha, dev_a, G.nz, nlam, l0, n_l, lay, W.dA[lay].p, W.stage, st));
+                have_a[lay] = true;
+            }
+            VRT_TRY(reg_boundary(G, W, down ? I0_down : I0_up, nlam, l0, n_l, lay, down, st));
+            VRT_CUDA(cudaEventRecord(ev.a));
+            VRT_TRY(reg_plane_loop(G, W, D, n_sweeps, n_l, W.dS[lay].p, W.dA[lay].p, W.dI.p, st, nullptr));
+            VRT_CUDA(cudaEventRecord(ev.b));
+            VRT_TRY(reg_store(G, W.dI.p, Jd, true, J_ld, J_l0, n_l, lay, q->weights[i], n_acc > 0, W.stage, st));
+            n_acc++;
+            VRT_CUDA(cudaDeviceSynchronize());
+            float ms = 0;
+            VRT_CUDA(cudaEventElapsedTime(&ms, ev.a, ev.b));
+            st->sweep_ms += ms;
+            st->visits += (double)(G.nz - 1) * (double)(G.nx - 2) * (double)(G.ny - 2) * (double)n_l;
+        }
+        if (n_acc == 0) {   // no direction contributes: J = zero(S)
+            if (dev_J && n_l == nlam) VRT_CUDA(cudaMemset(J, 0, sizeof(double) * G.vol * nlam));
+            else if (dev_J) VRT_CUDA(cudaMemset2D(J + l0, sizeof(double) * nlam, 0, sizeof(double) * n_l, G.vol));
+            else VRT_CUDA(cudaMemset(W.dJ.p, 0, sizeof(double) * G.vol * n_l));
+        }
+        if (!dev_J) {
+            if (n_l == nlam) VRT_CUDA(cudaMemcpy(J, W.dJ.p, sizeof(double) * G.vol * nlam, cudaMemcpyDeviceToHost));
+            else VRT_CUDA(cudaMemcpy2D(J + l0, sizeof(double) * nlam, W.dJ.p, sizeof(double) * n_l, sizeof(double) * n_l, G.vol, cudaMemcpyDeviceToHost));
+        }
+    }
+    return VRT_OK;
+}
+
+// plane iz of a (nz, nx, ny) column-major array -> contiguous (nx, ny)
+__global__ void k_reg_take_plane(const double* __restrict__ a, int64_t nz, int64_t iz, int64_t plane, double* __restrict__ out) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < plane) out[i] = a[iz + nz * i];
+}
+
+// host copy of a quadrature table whose arrays may live on the device
+struct RegQuad {
+    std::vector<double> w, t, p;
+    vrt_quadrature q;
+    int init(const vrt_quadrature* in) {
+        const size_t n = (size_t)in->n_dirs;
+        w.resize(n); t.resize(n); p.resize(n);
+        VRT_CUDA(cudaMemcpy(w.data(), in->weights, sizeof(double) * n, cudaMemcpyDefault));
+        VRT_CUDA(cudaMemcpy(t.data(), in->theta, sizeof(double) * n, cudaMemcpyDefault));
+        VRT_CUDA(cudaMemcpy(p.data(), in->phi, sizeof(double) * n, cudaMemcpyDefault));
+        q.n_dirs = in->n_dirs; q.weights = w.data(); q.theta = t.data(); q.phi = p.data();
+        return VRT_OK;
+    }
+};
+
+int reg_read_diff(RegWorkspace& W, double* diff) {
+    unsigned long long bits = 0;
+    int isn = 0;
+    VRT_CUDA(cudaMemcpy(&bits, W.diff_bits.p, sizeof(bits), cudaMemcpyDeviceToHost));
+    VRT_CUDA(cudaMemcpy(&isn, W.diff_nan.p, sizeof(isn), cudaMemcpyDeviceToHost));
+    double d;
+    memcpy(&d, &bits, sizeof(d));
+    *diff = isn ? NAN : d;   // Julia's maximum propagates NaN; `NaN > ϵ` is false and ends the loop
     return VRT_OK;
 }
 
@@ -309,179 +646,146 @@ using namespace vrt;
 extern "C" int vrt_regular_formal_solve(int64_t nz, int64_t nx, int64_t ny, const double* z, const double* x, const double* y,
                                         const double k[3], int32_t down, int32_t n_sweeps, int64_t nlam, const double* S,
                                         const double* alpha, const double* I0, double* I_out, int32_t* plane_branch) {
-    if (!z || !x || !y || !k || !S || !alpha || !I0 || !I_out || nlam <= 0 || nz < 2 || nx < 3 || ny < 3 || n_sweeps < 1) {
-        set_error("vrt_regular_formal_solve: bad arguments");
+    const char* who = "vrt_regular_formal_solve";
+    if (!k || !S || !alpha || !I0 || !I_out || nlam <= 0 || n_sweeps < 1) {
+        set_error("%s: bad arguments", who);
         return VRT_E_INVALID;
     }
-    if (nx > 1026 || ny > 1026) {
-        set_error("vrt_regular_formal_solve: nx, ny <= 1026 (one thread per interior point of a row in the recurrence)");
-        return VRT_E_INVALID;
-    }
-    if (!(k[0] == k[0]) || !(k[1] == k[1]) || !(k[2] == k[2]) || k[0] == 0.0) {
-        set_error("vrt_regular_formal_solve: direction must be finite with k[0] != 0");
-        return VRT_E_INVALID;
-    }
-    int ndev = 0;
-    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
-        cudaGetLastError();
-        set_error("vrt_regular_formal_solve: no CUDA device (this library has no CPU path)");
-        return VRT_E_CUDA;
-    }
-    std::vector<double> hz(nz), hx(nx), hy(ny);
-    VRT_TRY(host_copy(hz.data(), z, nz));
-    VRT_TRY(host_copy(hx.data(), x, nx));
-    VRT_TRY(host_copy(hy.data(), y, ny));
-    // characteristics.jl:34-40: path lengths to the x and y faces, xy_intersect signs
-    const double dx = hx[1] - hx[0], dy = hy[1] - hy[0];
-    const double r_x = fabs(dx / k[1]), r_y = fabs(dy / k[2]);
-    int sx = 1, sy = 1;
-    if (k[1] > 0 && k[2] > 0) { sx = -1; sy = -1; }
-    else if (k[1] < 0 && k[2] > 0) { sx = 1; sy = -1; }
-    else if (k[1] < 0 && k[2] < 0) { sx = 1; sy = 1; }
-    else if (k[1] > 0 && k[2] < 0) { sx = -1; sy = 1; }
-    // argmin([r_z, r_x, r_y]) takes the first minimum: a sideways plane is xz only when r_y < r_x strictly
-    RegPlane P;
-    P.par_is_x = (r_y < r_x) ? 1 : 0;
-    P.np = (int)(P.par_is_x ? nx : ny);
-    P.ns = (int)(P.par_is_x ? ny : nx);
-    P.sgn_j = P.par_is_x ? sx : sy;
-    P.sgn_s = P.par_is_x ? sy : sx;
-    P.kz = k[0];
-    P.kj = P.par_is_x ? k[1] : k[2];
-    P.ks = P.par_is_x ? k[2] : k[1];
-    const double r_side = P.par_is_x ? r_y : r_x;
-
-    const size_t plane = (size_t)nx * ny;
-    const size_t vol = plane * nz;
-    const bool dev_S = is_device_ptr(S), dev_a = is_device_ptr(alpha), dev_I0 = is_device_ptr(I0), dev_out = is_device_ptr(I_out);
+    RegGeom G;
+    VRT_TRY(reg_check_geom(who, nz, nx, ny, z, x, y, &G));
+    RegDir D;
+    VRT_TRY(reg_dir_setup(who, G, k, down, &D));
+    const int lay = D.P.par_is_x;
+    const bool dev_S = is_device_ptr(S), dev_a = is_device_ptr(alpha), dev_out = is_device_ptr(I_out);
     const bool need_stage = !(dev_S && dev_a && dev_out);
     std::lock_guard<std::mutex> lock(g_reg_mu);
-    if (!g_reg_ws) g_reg_ws = new RegWorkspace();
-    RegWorkspace& W = *g_reg_ws;
-    int cur_dev = 0;
-    VRT_CUDA(cudaGetDevice(&cur_dev));
-    if (W.device != cur_dev) { W.release(); W.device = cur_dev; }
-    size_t free_b = 0, total_b = 0;
-    VRT_CUDA(cudaMemGetInfo(&free_b, &total_b));
-    free_b += W.bytes();   // what the workspace already holds is ours to reuse
-    const double per_lam = 8.0 * ((3.0 + (need_stage ? 1.0 : 0.0)) * vol + 4.0 * plane);
-    int64_t lc = (int64_t)std::min<double>((double)nlam, floor(0.9 * (double)free_b / per_lam));
-    if (const char* e = getenv("VRT_REG_LAM_CHUNK")) lc = std::max<int64_t>(1, std::min<int64_t>(lc, atoll(e)));
-    if (lc < 1) {
-        set_error("vrt_regular_formal_solve: one wavelength of a %lld x %lld x %lld grid needs %.1f GB, %.1f GB free",
-                  (long long)nz, (long long)nx, (long long)ny, per_lam / 1e9, free_b / 1e9);
-        return VRT_E_NOMEM;
-    }
-    lc = std::min<int64_t>(lc, 65535);
-    DevBuf<double>&dS = W.dS, &dA = W.dA, &dI = W.dI, &stage = W.stage, &stage0 = W.stage0, &cA = W.cA, &cB = W.cB, &cC = W.cC,
-                  &dcj = W.dcj, &dcs = W.dcs;
+    RegWorkspace* Wp = nullptr;
+    VRT_TRY(reg_workspace(&Wp));
+    RegWorkspace& W = *Wp;
+    int64_t lc = 0;
+    VRT_TRY(reg_plan_chunk(who, G, W, nlam, 3.0 + (need_stage ? 1.0 : 0.0), 4.0, &lc));
     {
-        const size_t need_vol = vol * lc, need_pl = plane * lc;
+        const size_t need_vol = G.vol * lc;
         // a grow of one buffer must not fail because the others hold stale, larger-than-needed space
-        const bool grow = dS.n < need_vol || dA.n < need_vol || dI.n < need_vol || (need_stage && stage.n < need_vol) ||
-                          (!dev_I0 && stage0.n < need_pl) || cA.n < need_pl || cB.n < need_pl || cC.n < need_pl;
+        const bool grow = W.dS[lay].n < need_vol || W.dA[lay].n < need_vol || W.dI.n < need_vol || (need_stage && W.stage.n < need_vol);
         if (grow) W.release();
-        VRT_TRY(dS.ensure(need_vol)); VRT_TRY(dA.ensure(need_vol)); VRT_TRY(dI.ensure(need_vol));
-        if (need_stage) VRT_TRY(stage.ensure(need_vol));
-        if (!dev_I0) VRT_TRY(stage0.ensure(need_pl));
-        VRT_TRY(cA.ensure(need_pl)); VRT_TRY(cB.ensure(need_pl)); VRT_TRY(cC.ensure(need_pl));
-        VRT_TRY(dcj.ensure(P.np)); VRT_TRY(dcs.ensure(P.ns));
+        VRT_TRY(W.dS[lay].ensure(need_vol)); VRT_TRY(W.dA[lay].ensure(need_vol)); VRT_TRY(W.dI.ensure(need_vol));
+        VRT_TRY(reg_common_buffers(G, W, lc));
     }
-    VRT_CUDA(cudaMemcpy(dcj.p, P.par_is_x ? hx.data() : hy.data(), sizeof(double) * P.np, cudaMemcpyHostToDevice));
-    VRT_CUDA(cudaMemcpy(dcs.p, P.par_is_x ? hy.data() : hx.data(), sizeof(double) * P.ns, cudaMemcpyHostToDevice));
-
     SweepStats stats;
     std::vector<int32_t> branch(nz, 0);
-    cudaEvent_t ev0, ev1;
-    VRT_CUDA(cudaEventCreate(&ev0));
-    VRT_CUDA(cudaEventCreate(&ev1));
-    struct EvGuard { cudaEvent_t a, b; ~EvGuard() { cudaEventDestroy(a); cudaEventDestroy(b); } } evg{ev0, ev1};
-
-    const dim3 tb(32, 8);
-    // user array (host or device) -> internal layout of the current chunk
-    auto load = [&](const double* src, bool on_dev, int64_t nz_, double* dst, DevBuf<double>& stg, int64_t l0, int64_t n_l) -> int {
-        const double* s_dev = src;
-        int64_t ld = nlam, lo = l0;
-        const size_t rows = (size_t)nz_ * plane;
-        if (!on_dev) {
-            if (n_l == nlam) VRT_CUDA(cudaMemcpy(stg.p, src, sizeof(double) * rows * nlam, cudaMemcpyHostToDevice));
-            else VRT_CUDA(cudaMemcpy2D(stg.p, sizeof(double) * n_l, src + l0, sizeof(double) * nlam, sizeof(double) * n_l, rows, cudaMemcpyHostToDevice));
-            s_dev = stg.p; ld = n_l; lo = 0;
-        }
-        const dim3 grid((unsigned)((n_l * nz_ + 31) / 32), (unsigned)((P.np + 31) / 32), (unsigned)P.ns);
-        k_reg_transpose<1><<<grid, tb>>>(s_dev, dst, ld, lo, (int)n_l, nz_, nx, ny, P.par_is_x);
-        VRT_CUDA(cudaGetLastError());
-        stats.kernels += 1;
-        return VRT_OK;
-    };
-
+    EvPair ev;
+    VRT_TRY(ev.create());
     for (int64_t l0 = 0; l0 < nlam; l0 += lc) {
         const int64_t n_l = std::min<int64_t>(lc, nlam - l0);
-        P.lc = (int)n_l;
-        const size_t pst = plane * n_l;   // plane stride of the internal arrays
-        VRT_TRY(load(S, dev_S, nz, dS.p, stage, l0, n_l));
-        VRT_CUDA(cudaDeviceSynchronize());   // `stage` is reused
-        VRT_TRY(load(alpha, dev_a, nz, dA.p, stage, l0, n_l));
-        const int64_t zb = down ? nz - 1 : 0;
+        VRT_TRY(reg_load(G, S, dev_S, nz, nlam, l0, n_l, lay, W.dS[lay].p, W.stage, &stats));
+        VRT_TRY(reg_load(G, alpha, dev_a, nz, nlam, l0, n_l, lay, W.dA[lay].p, W.stage, &stats));
         // I[zb, :, :] = I_0 (characteristics.jl:45 / :133), ghost columns as the caller filled them
-        VRT_TRY(load(I0, dev_I0, 1, dI.p + pst * zb, stage0, l0, n_l));
-        VRT_CUDA(cudaEventRecord(ev0));
-        for (int64_t step = 1; step < nz; step++) {
-            const int64_t idz = down ? nz - 1 - step : step;        // 0-based plane being solved
-            const int64_t idu = down ? idz + 1 : idz - 1;           // upwind plane
-            const double dz = down ? hz[idz + 1] - hz[idz] : hz[idz] - hz[idz - 1];
-            const double r_z = fabs(dz / k[0]);
-            int cut = 1;
-            double best = r_z;
-            if (r_x < best) { best = r_x; cut = 2; }
-            if (r_y < best) { best = r_y; cut = 3; }
-            branch[idz] = cut;
-            double* Ic = dI.p + pst * idz;
-            const double* Iu = dI.p + pst * idu;
-            if (cut == 1) {
-                const dim3 grid((unsigned)((P.np * P.ns + 255) / 256), (unsigned)n_l);
-                k_reg_xy<<<grid, 256>>>(P, hz[idu] - hz[idz], dcj.p, dcs.p, dS.p + pst * idz, dA.p + pst * idz, dS.p + pst * idu,
-                                        dA.p + pst * idu, Iu, Ic);
-                stats.kernels += 1;
-            } else {
-                const int up = down ? 0 : 1;
-                const int64_t izl = up ? idz - 1 : idz, izu = izl + 1;
-                const int64_t izc = P.par_is_x ? izu : idz;          // Q13: xz takes the centre from the upper plane
-                const dim3 grid((unsigned)((P.np * P.ns + 255) / 256), (unsigned)n_l);
-                k_reg_coef<<<grid, 256>>>(P, up, hz[idz], hz[izl], hz[izu], dcj.p, dcs.p, dS.p + pst * izl, dS.p + pst * izu,
-                                          dA.p + pst * izl, dA.p + pst * izu, dS.p + pst * izc, dA.p + pst * izc, Iu, cA.p, cB.p, cC.p);
-                const int threads = ((P.np - 2 + 31) / 32) * 32;
-                const size_t rec_smem = sizeof(double) * 2 * P.np;
-                if (threads <= 512) k_reg_rec<512, REG_PF><<<(unsigned)n_l, threads, rec_smem>>>(P, n_sweeps, cA.p, cB.p, cC.p, Ic);
-                else k_reg_rec<1024, REG_PF / 3><<<(unsigned)n_l, threads, rec_smem>>>(P, n_sweeps, cA.p, cB.p, cC.p, Ic);
-                stats.kernels += 2;
-                stats.steps += (double)n_sweeps * (P.ns - 2);
-            }
-            VRT_CUDA(cudaGetLastError());
-        }
-        VRT_CUDA(cudaEventRecord(ev1));
-        // internal -> caller's layout
-        {
-            double* d_dst = dev_out ? I_out : stage.p;
-            const int64_t ld = dev_out ? nlam : n_l, lo = dev_out ? l0 : 0;
-            const dim3 grid((unsigned)((n_l * nz + 31) / 32), (unsigned)((P.np + 31) / 32), (unsigned)P.ns);
-            k_reg_transpose<0><<<grid, tb>>>(dI.p, d_dst, ld, lo, (int)n_l, nz, nx, ny, P.par_is_x);
-            VRT_CUDA(cudaGetLastError());
-            stats.kernels += 1;
-            if (!dev_out) {
-                if (n_l == nlam) VRT_CUDA(cudaMemcpy(I_out, stage.p, sizeof(double) * vol * nlam, cudaMemcpyDeviceToHost));
-                else VRT_CUDA(cudaMemcpy2D(I_out + l0, sizeof(double) * nlam, stage.p, sizeof(double) * n_l, sizeof(double) * n_l, vol, cudaMemcpyDeviceToHost));
-            }
-        }
+        VRT_TRY(reg_boundary(G, W, I0, nlam, l0, n_l, lay, D.down, &stats));
+        VRT_CUDA(cudaEventRecord(ev.a));
+        VRT_TRY(reg_plane_loop(G, W, D, n_sweeps, n_l, W.dS[lay].p, W.dA[lay].p, W.dI.p, &stats, branch.data()));
+        VRT_CUDA(cudaEventRecord(ev.b));
+        VRT_TRY(reg_store(G, W.dI.p, I_out, dev_out, nlam, l0, n_l, lay, 1.0, 0, W.stage, &stats));
         VRT_CUDA(cudaDeviceSynchronize());
         float ms = 0;
-        VRT_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
+        VRT_CUDA(cudaEventElapsedTime(&ms, ev.a, ev.b));
         stats.sweep_ms += ms;
     }
-    (void)r_side;
     stats.visits = (double)(nz - 1) * (double)(nx - 2) * (double)(ny - 2) * (double)nlam;
     g_last_stats = stats;
     if (plane_branch) VRT_CUDA(cudaMemcpy(plane_branch, branch.data(), sizeof(int32_t) * nz, cudaMemcpyDefault));
+    return VRT_OK;
+}
+
+extern "C" int vrt_regular_mean_intensity(int64_t nz, int64_t nx, int64_t ny, const double* z, const double* x, const double* y,
+                                          const vrt_quadrature* quad, int32_t n_sweeps, int64_t nlam, const double* S,
+                                          const double* alpha, const double* I0_up, const double* I0_down, double* J) {
+    const char* who = "vrt_regular_mean_intensity";
+    if (!quad || quad->n_dirs <= 0 || !quad->weights || !quad->theta || !quad->phi || !S || !alpha || !J || nlam <= 0 || n_sweeps < 1) {
+        set_error("%s: bad arguments", who);
+        return VRT_E_INVALID;
+    }
+    RegGeom G;
+    VRT_TRY(reg_check_geom(who, nz, nx, ny, z, x, y, &G));
+    std::lock_guard<std::mutex> lock(g_reg_mu);
+    RegWorkspace* Wp = nullptr;
+    VRT_TRY(reg_workspace(&Wp));
+    SweepStats stats;
+    RegQuad hq;
+    VRT_TRY(hq.init(quad));
+    VRT_TRY(reg_mean_intensity(who, G, *Wp, &hq.q, n_sweeps, nlam, S, alpha, I0_up, I0_down, J, nullptr, &stats));
+    g_last_stats = stats;
+    return VRT_OK;
+}
+
+extern "C" int vrt_regular_lambda_iterate(int64_t nz, int64_t nx, int64_t ny, const double* z, const double* x, const double* y,
+                                          const vrt_quadrature* quad, int32_t n_sweeps, const double* alpha, const double* eps_l,
+                                          const double* B0, double eps, int32_t maxiter, vrt_iter_cb cb, void* user, double* S_out,
+                                          double* J_out, vrt_result* out) {
+    const char* who = "vrt_regular_lambda_iterate";
+    if (!quad || quad->n_dirs <= 0 || !quad->weights || !quad->theta || !quad->phi || !alpha || !eps_l || !B0 || n_sweeps < 1) {
+        set_error("%s: bad arguments", who);
+        return VRT_E_INVALID;
+    }
+    auto t_begin = std::chrono::steady_clock::now();
+    RegGeom G;
+    VRT_TRY(reg_check_geom(who, nz, nx, ny, z, x, y, &G));
+    std::lock_guard<std::mutex> lock(g_reg_mu);
+    RegWorkspace* Wp = nullptr;
+    VRT_TRY(reg_workspace(&Wp));
+    RegWorkspace& W = *Wp;
+    RegQuad hq;
+    VRT_TRY(hq.init(quad));
+    const int64_t n = (int64_t)G.vol;
+    // state in the caller's layout, resident for the whole loop
+    DevBuf<double> dS, dJ, dal, dep, dB, dI0;
+    VRT_TRY(dS.alloc(n)); VRT_TRY(dJ.alloc(n)); VRT_TRY(dal.alloc(n)); VRT_TRY(dep.alloc(n)); VRT_TRY(dB.alloc(n)); VRT_TRY(dI0.alloc(G.plane));
+    VRT_TRY(copy_in(dal.p, alpha, sizeof(double) * n)); VRT_TRY(copy_in(dep.p, eps_l, sizeof(double) * n)); VRT_TRY(copy_in(dB.p, B0, sizeof(double) * n));
+    VRT_TRY(W.diff_bits.ensure(1)); VRT_TRY(W.diff_nan.ensure(1));
+    // S_new = B_0 (lambda_continuum.jl:84-85); bottom boundary blackbody_λ(500 nm, T[1,:,:]) = B_0[1,:,:] (:16)
+    VRT_CUDA(cudaMemcpy(dS.p, dB.p, sizeof(double) * n, cudaMemcpyDeviceToDevice));
+    VRT_CUDA(cudaMemset(dJ.p, 0, sizeof(double) * n));
+    k_reg_take_plane<<<(unsigned)((G.plane + 255) / 256), 256>>>(dB.p, nz, 0, (int64_t)G.plane, dI0.p);
+    VRT_CUDA(cudaGetLastError());
+    // first criterion: S_old = zero(S_new) (:87), over `thick` = ε > 1e-4 (:81)
+    VRT_CUDA(cudaMemset(W.diff_bits.p, 0, sizeof(unsigned long long)));
+    VRT_CUDA(cudaMemset(W.diff_nan.p, 0, sizeof(int)));
+    VRT_TRY(continuum_criterion(n, dS.p, nullptr, dep.p, W.diff_bits.p, W.diff_nan.p));
+    double diff = 0;
+    VRT_TRY(reg_read_diff(W, &diff));
+    int i = 0;
+    bool alpha_ready[2] = {false, false};
+    SweepStats total;
+    while (diff > eps && i < maxiter) {
+        auto t0 = std::chrono::steady_clock::now();
+        SweepStats stats;
+        vrt_iter_info info;
+        memset(&info, 0, sizeof(info));
+        info.diff = diff;
+        VRT_TRY(reg_mean_intensity(who, G, W, &hq.q, n_sweeps, 1, dS.p, dal.p, dI0.p, nullptr, dJ.p, alpha_ready, &stats));
+        info.t_sweep_ms = stats.sweep_ms;
+        VRT_CUDA(cudaMemset(W.diff_bits.p, 0, sizeof(unsigned long long)));
+        VRT_CUDA(cudaMemset(W.diff_nan.p, 0, sizeof(int)));
+        VRT_TRY(continuum_source_update(n, dB.p, dep.p, dJ.p, dS.p, W.diff_bits.p, W.diff_nan.p));
+        stats.kernels += 1;
+        VRT_TRY(reg_read_diff(W, &diff));
+        i++;
+        info.iteration = i;
+        info.updates = stats.visits;
+        info.t_total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        total.kernels += stats.kernels; total.visits += stats.visits; total.steps += stats.steps; total.sweep_ms += stats.sweep_ms;
+        if (cb && cb(&info, user) != 0) break;
+    }
+    if (S_out) VRT_TRY(copy_out(S_out, dS.p, sizeof(double) * n));
+    if (J_out) VRT_TRY(copy_out(J_out, dJ.p, sizeof(double) * n));
+    VRT_CUDA(cudaDeviceSynchronize());
+    g_last_stats = total;
+    if (out) {
+        out->iterations = i;
+        out->converged = !(diff > eps);
+        out->diff = diff;
+        out->seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_begin).count();
+    }
     return VRT_OK;
 }
 

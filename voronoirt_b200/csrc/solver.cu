@@ -263,6 +263,19 @@ __global__ void k_criterion(int64_t n, int64_t nlam, const double* __restrict__ 
     block_max_nan(dmax, isn, diff_bits, diff_nan);
 }
 
+// single-wavelength forms of the two kernels above for the regular-grid Λ-iteration (regular.cu): S, J, eps, B0 are n-vectors
+int continuum_criterion(int64_t n, const double* S_new, const double* S_old, const double* eps, unsigned long long* diff_bits, int* diff_nan) {
+    k_criterion<<<nblocks(n, 256), 256>>>(n, 1, S_new, S_old, eps, 1, diff_bits, diff_nan);
+    VRT_CUDA(cudaGetLastError());
+    return VRT_OK;
+}
+int continuum_source_update(int64_t n, const double* B0, const double* eps, const double* J, double* S, unsigned long long* diff_bits,
+                            int* diff_nan) {
+    k_source_update<<<nblocks(n, 256), 256>>>(n, 1, nullptr, nullptr, B0, eps, J, S, 1, diff_bits, diff_nan);
+    VRT_CUDA(cudaGetLastError());
+    return VRT_OK;
+}
+
 __global__ void k_planck_rows(int64_t n, int64_t nlam, const double* __restrict__ lam, const double* __restrict__ T, double* __restrict__ S) {
     int64_t total = n * nlam;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {

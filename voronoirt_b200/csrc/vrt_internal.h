@@ -176,5 +176,9 @@ int sweep_scratch_rows(const DirSchedule* sch, int s);
 // misc kernels (physics.cu)
 int permute_rows(const double* src, double* dst, const int32_t* map, int64_t n, int64_t nlam, int gather, cudaStream_t st);
 extern thread_local SweepStats g_last_stats;
+// S_new = (1-ε)J + εB with the criterion fused / the criterion alone, one wavelength (solver.cu; used by regular.cu)
+int continuum_criterion(int64_t n, const double* S_new, const double* S_old, const double* eps, unsigned long long* diff_bits, int* diff_nan);
+int continuum_source_update(int64_t n, const double* B0, const double* eps, const double* J, double* S, unsigned long long* diff_bits,
+                            int* diff_nan);
 
 }  // namespace vrt
