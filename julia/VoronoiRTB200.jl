@@ -1,6 +1,7 @@
 # VoronoiRTB200.jl — the Julia-side binding a VoronoiRT maintainer adds to route the irregular-grid hot path
 # through libvrt.so.  Same function names and signatures as the reference (src/voronoi_utils.jl:36,
-# src/irregular_ray_tracing.jl:15,96, src/lambda_iteration.jl:60,207, src/rates.jl:154, src/populations.jl:191), so the
+# src/irregular_ray_tracing.jl:15,96, src/lambda_iteration.jl:60,207, src/rates.jl:154, src/populations.jl:191,
+# src/characteristics.jl:19,110, src/lambda_continuum.jl:1,58), so the
 # entry scripts (compare_searchlight.jl, compare_continuum.jl, compare_line.jl) run unchanged after
 #     include("VoronoiRTB200.jl"); using .VoronoiRTB200
 # NOTE: no Julia toolchain exists in the build image, so this file has not been executed here; it is the
@@ -141,6 +142,54 @@ function get_revised_populations(R::Array{<:Unitful.Frequency,3}, C::Array{<:Uni
     check(ccall((:vrt_get_revised_populations, libvrt), Cint, (Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
                 n, ustrip.(u"s^-1", R), ustrip.(u"s^-1", C), ustrip.(u"m^-3", atom_density), pops))
     return pops * u"m^-3"
+end
+
+# ---------------------------------------------------------------- regular grid (src/characteristics.jl:19-95, :110-180)
+# atmos is the reference's Atmosphere (src/atmosphere.jl:22-31): z, x, y with the periodic ghost columns in x and y.
+function _short_characteristics(k::Vector, S_0::Array{<:Any,3}, I_0::Matrix, α::Array{<:Any,3}, atmos, n_sweeps::Int, down::Int)
+    z = Float64.(ustrip.(u"m", atmos.z)); x = Float64.(ustrip.(u"m", atmos.x)); y = Float64.(ustrip.(u"m", atmos.y))
+    S = Float64.(ustrip.(u"kW*m^-2*nm^-1", S_0)); I0 = Float64.(ustrip.(u"kW*m^-2*nm^-1", I_0)); a = Float64.(ustrip.(u"m^-1", α))
+    I = similar(S)
+    kk = Float64.(k)
+    check(ccall((:vrt_regular_formal_solve, libvrt), Cint,
+                (Int64, Int64, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int32, Int32, Int64,
+                 Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}),
+                length(z), length(x), length(y), z, x, y, kk, down, n_sweeps, 1, S, a, I0, I, C_NULL))
+    return I * u"kW*m^-2*nm^-1"
+end
+short_characteristics_up(k, S_0, I_0, α, atmos; n_sweeps=3) = _short_characteristics(k, S_0, I_0, α, atmos, n_sweeps, 0)
+short_characteristics_down(k, S_0, I_0, α, atmos; n_sweeps=3) = _short_characteristics(k, S_0, I_0, α, atmos, n_sweeps, 1)
+
+# J_λ_regular, continuum form (src/lambda_continuum.jl:1-24); I_0 = blackbody_λ.(500u"nm", atmos.temperature[1,:,:]) (:16)
+function J_λ_regular(S_λ::AbstractArray, α_cont::AbstractArray, atmos, quadrature::String; I_0)
+    tab = readdlm_quadrature(quadrature)
+    w, th, ph = tab[:, 1], tab[:, 2], tab[:, 3]
+    q = Ref(vrt_quadrature(length(w), pointer(w), pointer(th), pointer(ph)))
+    z = Float64.(ustrip.(u"m", atmos.z)); x = Float64.(ustrip.(u"m", atmos.x)); y = Float64.(ustrip.(u"m", atmos.y))
+    S = Float64.(ustrip.(u"kW*m^-2*nm^-1", S_λ)); a = Float64.(ustrip.(u"m^-1", α_cont)); I0 = Float64.(ustrip.(u"kW*m^-2*nm^-1", I_0))
+    J = similar(S)
+    GC.@preserve w th ph check(ccall((:vrt_regular_mean_intensity, libvrt), Cint,
+                (Int64, Int64, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ref{vrt_quadrature}, Int32, Int64,
+                 Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+                length(z), length(x), length(y), z, x, y, q, 3, 1, S, a, I0, C_NULL, J))
+    return J * u"kW*m^-2*nm^-1"
+end
+
+# Λ_regular, continuum (src/lambda_continuum.jl:58-107): α_cont, ε_λ, B_0 as computed at :66-85
+function Λ_regular(ϵ::AbstractFloat, maxiter::Integer, atmos, quadrature::String; α_cont, ε_λ, B_0)
+    tab = readdlm_quadrature(quadrature)
+    w, th, ph = tab[:, 1], tab[:, 2], tab[:, 3]
+    q = Ref(vrt_quadrature(length(w), pointer(w), pointer(th), pointer(ph)))
+    z = Float64.(ustrip.(u"m", atmos.z)); x = Float64.(ustrip.(u"m", atmos.x)); y = Float64.(ustrip.(u"m", atmos.y))
+    a = Float64.(ustrip.(u"m^-1", α_cont)); e = Float64.(ε_λ); B = Float64.(ustrip.(u"kW*m^-2*nm^-1", B_0))
+    S = similar(B); J = similar(B)
+    res = Ref(vrt_result(0, 0, 0.0, 0.0))
+    GC.@preserve w th ph check(ccall((:vrt_regular_lambda_iterate, libvrt), Cint,
+                (Int64, Int64, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ref{vrt_quadrature}, Int32, Ptr{Float64}, Ptr{Float64},
+                 Ptr{Float64}, Float64, Int32, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ref{vrt_result}),
+                length(z), length(x), length(y), z, x, y, q, 3, a, e, B, ϵ, maxiter, C_NULL, C_NULL, S, J, res))
+    res[].converged == 1 ? println("Converged in $(res[].iterations) iterations") : println("Did not converge inside scope")
+    return J * u"kW*m^-2*nm^-1", S * u"kW*m^-2*nm^-1", α_cont
 end
 
 function readdlm_quadrature(fname)

@@ -299,10 +299,13 @@ struct RegWorkspace {
     size_t bytes() const {
         return 8 * (dS[0].n + dS[1].n + dA[0].n + dA[1].n + dI.n + stage.n + stage0.n + cA.n + cB.n + cC.n + dx.n + dy.n + dJ.n);
     }
-    void release() {
+    void release_arrays() {   // before a grow: the large buffers only
         for (int i = 0; i < 2; i++) { dS[i].release(); dA[i].release(); }
-        dI.release(); stage.release(); stage0.release(); cA.release(); cB.release(); cC.release();
-        dx.release(); dy.release(); dJ.release(); diff_bits.release(); diff_nan.release();
+        dI.release(); stage.release(); stage0.release(); cA.release(); cB.release(); cC.release(); dJ.release();
+    }
+    void release() {
+        release_arrays();
+        dx.release(); dy.release(); diff_bits.release(); diff_nan.release();
     }
 };
 std::mutex g_reg_mu;
@@ -546,7 +549,7 @@ int reg_mean_intensity(const char* who, const RegGeom& G, RegWorkspace& W, const
         bool grow = W.dI.n < need_vol || (need_stage && W.stage.n < need_vol) || (!dev_J && W.dJ.n < need_vol);
         for (int i = 0; i < 2; i++) grow = grow || (W.dS[i].p && W.dS[i].n < need_vol) || (W.dA[i].p && W.dA[i].n < need_vol);
         if (grow) {
-            W.release();
+            W.release_arrays();
             if (alpha_ready) alpha_ready[0] = alpha_ready[1] = false;
         }
         VRT_TRY(W.dI.ensure(need_vol));
@@ -668,7 +671,7 @@ extern "C" int vrt_regular_formal_solve(int64_t nz, int64_t nx, int64_t ny, cons
         const size_t need_vol = G.vol * lc;
         // a grow of one buffer must not fail because the others hold stale, larger-than-needed space
         const bool grow = W.dS[lay].n < need_vol || W.dA[lay].n < need_vol || W.dI.n < need_vol || (need_stage && W.stage.n < need_vol);
-        if (grow) W.release();
+        if (grow) W.release_arrays();
         VRT_TRY(W.dS[lay].ensure(need_vol)); VRT_TRY(W.dA[lay].ensure(need_vol)); VRT_TRY(W.dI.ensure(need_vol));
         VRT_TRY(reg_common_buffers(G, W, lc));
     }
