@@ -208,6 +208,16 @@ int vrt_regular_lambda_iterate(int64_t nz, int64_t nx, int64_t ny, const double*
                                const double* B0, double eps, int32_t maxiter, vrt_iter_cb cb, void* user, double* S_out,
                                double* J_out, vrt_result* out);
 
+/* A vrt_grid over the regular Cartesian atmosphere (atmosphere.jl:22-31): cell c = iz + nz*(ix + nx*iy), i.e. the memory
+ * order of the reference's (nz, nx, ny) arrays, x and y with their ghost columns.  The handle feeds the same Λ-iteration
+ * engine as a Voronoi grid — vrt_solver_create_line / _continuum, vrt_mean_intensity (J_λ_regular, lambda_iteration.jl:1-58),
+ * vrt_calculate_R (rates.jl:96-143), vrt_lambda_iterate (Λ_regular, lambda_iteration.jl:116-205 with criterion :299-323),
+ * vrt_get_state / vrt_set_state — with every per-site array being the flattened (nz, nx, ny) array, S and J
+ * nlam x nz x nx x ny, populations nz x nx x ny x 3.  The formal solutions run through the plane walk of
+ * vrt_regular_formal_solve.  Layer / stencil / schedule queries and direction or cell shards return VRT_E_STATE /
+ * VRT_E_INVALID on such a handle.  Destroy with vrt_grid_destroy. */
+int vrt_regular_grid_create(int64_t nz, int64_t nx, int64_t ny, const double* z, const double* x, const double* y, vrt_grid** out);
+
 /* the regular-grid entries keep their device workspace (3-6 internal copies of one wavelength chunk) between calls;
  * this frees it, e.g. before handing the GPU to an irregular-grid solver. */
 int vrt_regular_release_workspace(void);

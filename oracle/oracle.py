@@ -273,3 +273,28 @@ def lambda_regular(z, x, y, weights, theta, phi, alpha, eps_l, B0, eps=1e-3, max
                                   _p(weights), _p(theta), _p(phi), C.c_int(n_sweeps), C.c_double(eps), C.c_int(maxiter),
                                   _p(alpha), _p(eps_l), _p(B0), _p(S), _p(J), _p(conv))
     return J, S, conv, it
+
+
+def J_lambda_regular(z, x, y, line, lam, sd, quad, S, pops, n_sweeps=3):
+    """lambda_iteration.jl:1-58.  S (n, nlam) with n = nz*nx*ny cells in column-major (nz, nx, ny) order; pops (3, n)."""
+    z, x, y, lam = map(f64, (z, x, y, lam))
+    S = f64(S)
+    pops = f64(pops)
+    J = np.zeros_like(S)
+    damping = np.zeros_like(S)
+    lib().orc_J_lambda_regular(C.c_int64(len(z)), C.c_int64(len(x)), C.c_int64(len(y)), _p(z), _p(x), _p(y), C.byref(line), _p(lam),
+                               C.byref(sd), C.byref(quad), C.c_int(n_sweeps), _p(S), _p(pops), _p(J), _p(damping))
+    return J, damping
+
+
+def lambda_regular_line(z, x, y, line, lam, sd, quad, S0, pops0, eps=1e-3, maxiter=150, n_sweeps=3):
+    """lambda_iteration.jl:116-205 -> (J, S, pops, convergence, iterations)"""
+    z, x, y, lam = map(f64, (z, x, y, lam))
+    S = f64(S0).copy()
+    pops = f64(pops0).copy()
+    J = np.zeros_like(S)
+    conv = np.zeros(maxiter + 1)
+    it = lib().orc_lambda_regular_line(C.c_int64(len(z)), C.c_int64(len(x)), C.c_int64(len(y)), _p(z), _p(x), _p(y), C.byref(line),
+                                       _p(lam), C.byref(sd), C.byref(quad), C.c_int(n_sweeps), C.c_double(eps), C.c_int(maxiter),
+                                       _p(S), _p(J), _p(pops), _p(conv))
+    return J, S, pops, conv, it

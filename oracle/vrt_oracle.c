@@ -765,6 +765,88 @@ int orc_lambda_voronoi(const orc_sites* s, const vrt_line* line, const double* l
     return i;
 }
 
+/* ---- regular-grid twins of the line path.  The per-cell physics is the same code; only the formal solver differs
+ * (orc_short_characteristics, vrt_oracle_regular.c).  Cells are the (nz, nx, ny) arrays flattened column-major. */
+void orc_short_characteristics(int64_t nz, int64_t nx, int64_t ny, const double* z, const double* x, const double* y,
+                               const double* k, int down, const double* S, const double* I_0, const double* al, int n_sweeps,
+                               double* I, int32_t* plane_out);
+
+/* J_λ_regular (line), src/lambda_iteration.jl:1-58: γ, damping (:13-21); per direction the Voigt profile with
+ * v_los = velocity . (-k) (line.jl:80-96,175-190), α_tot (:32-35), I_0 = B_λ(λ_l, T[1,:,:]) for θ > 90 (:38) or zero (:46). */
+void orc_J_lambda_regular(int64_t nz, int64_t nx, int64_t ny, const double* z, const double* x, const double* y,
+                          const vrt_line* line, const double* lambda, const vrt_site_data* sd, const vrt_quadrature* q,
+                          int n_sweeps, const double* S, const double* pops, double* J, double* damping) {
+    int64_t n = nz * nx * ny, nlam = line->nlam, plane = nx * ny;
+    for (int64_t i = 0; i < n * nlam; i++) J[i] = 0.0;
+    double* gamma = (double*)malloc(sizeof(double) * (size_t)n);
+    double* nHI = (double*)malloc(sizeof(double) * (size_t)n);
+    for (int64_t i = 0; i < n; i++) nHI[i] = pops[i] + pops[i + n];
+    orc_gamma_constant(line, n, sd->temperature, nHI, sd->electron_density, gamma);
+    for (int64_t i = 0; i < n; i++)
+        for (int64_t l = 0; l < nlam; l++) damping[l + nlam * i] = orc_damping(gamma[i], lambda[l], sd->doppler_width[i]);
+    double* vlos = (double*)malloc(sizeof(double) * (size_t)n);
+    double c_line = H_PLANCK * C_0 / (4 * PI * (line->lambda0 * 1e-9)); /* αline_λ, line.jl:219-225 */
+    for (int64_t d = 0; d < q->n_dirs; d++) {
+        double th = q->theta[d], ph = q->phi[d];
+        double k[3] = {cos(th * PI / 180), cos(ph * PI / 180) * sin(th * PI / 180), sin(ph * PI / 180) * sin(th * PI / 180)};
+        if (!(th > 90) && !(th < 90)) continue;
+        int down = !(th > 90);
+        for (int64_t i = 0; i < n; i++)
+            vlos[i] = sd->velocity_z[i] * (-k[0]) + sd->velocity_x[i] * (-k[1]) + sd->velocity_y[i] * (-k[2]);
+#pragma omp parallel
+        {
+            double* Sv = (double*)malloc(sizeof(double) * (size_t)n);
+            double* av = (double*)malloc(sizeof(double) * (size_t)n);
+            double* Iv = (double*)malloc(sizeof(double) * (size_t)n);
+            double* I0v = (double*)malloc(sizeof(double) * (size_t)plane);
+#pragma omp for schedule(dynamic, 1)
+            for (int64_t l = 0; l < nlam; l++) {
+                for (int64_t i = 0; i < n; i++) {
+                    double dD = sd->doppler_width[i];
+                    double v = (lambda[l] - line->lambda0 + line->lambda0 * vlos[i] / C_0) / dD; /* line.jl:91 */
+                    double prof = orc_voigt_profile(damping[l + nlam * i], v, dD * 1e-9);         /* m^-1 */
+                    av[i] = c_line * prof * (pops[i] * line->Bij - pops[i + n] * line->Bji) + sd->alpha_cont[i];
+                    Sv[i] = S[l + nlam * i];
+                }
+                for (int64_t i = 0; i < plane; i++) I0v[i] = down ? 0.0 : orc_B_lambda(lambda[l], sd->temperature[nz * i]);
+                orc_short_characteristics(nz, nx, ny, z, x, y, k, down, Sv, I0v, av, n_sweeps, Iv, NULL);
+                for (int64_t i = 0; i < n; i++) J[l + nlam * i] += q->weights[d] * Iv[i];
+            }
+            free(Sv); free(av); free(Iv); free(I0v);
+        }
+    }
+    free(gamma); free(nHI); free(vlos);
+}
+
+/* Λ_regular (line), src/lambda_iteration.jl:116-205 with criterion :299-323 */
+int orc_lambda_regular_line(int64_t nz, int64_t nx, int64_t ny, const double* z, const double* x, const double* y,
+                            const vrt_line* line, const double* lambda, const vrt_site_data* sd, const vrt_quadrature* q,
+                            int n_sweeps, double eps, int maxiter, double* S, double* J, double* pops, double* conv) {
+    int64_t n = nz * nx * ny, nlam = line->nlam;
+    size_t tot = (size_t)n * (size_t)nlam;
+    double* S_old = (double*)calloc(tot, sizeof(double));
+    double* damping = (double*)malloc(sizeof(double) * tot);
+    double* R = (double*)malloc(sizeof(double) * 9 * (size_t)n);
+    int i = 0;
+    for (;;) {
+        double diff = orc_criterion(S, S_old, (int64_t)tot, NULL, 1);
+        if (conv) conv[i] = diff;
+        if (!(diff > eps && i < maxiter)) break;
+        memcpy(S_old, S, sizeof(double) * tot);
+        orc_J_lambda_regular(nz, nx, ny, z, x, y, line, lambda, sd, q, n_sweeps, S_old, pops, J, damping);
+        for (int64_t c = 0; c < n; c++) {
+            double e = sd->destruction[c];
+            for (int64_t l = 0; l < nlam; l++)
+                S[l + nlam * c] = (1 - e) * J[l + nlam * c] + e * orc_B_lambda(lambda[l], sd->temperature[c]);
+        }
+        orc_calculate_R(line, lambda, n, sd->temperature, sd->doppler_width, J, damping, sd->lte_pops, R);
+        orc_get_revised_populations(n, R, sd->C, sd->hydrogen_density, pops);
+        i++;
+    }
+    free(S_old); free(damping); free(R);
+    return i;
+}
+
 /* Λ_voronoi (continuum), src/lambda_continuum.jl:109-160 with `criterion` over thick = ε > 1e-4 (:133,:181-198). */
 int orc_lambda_continuum(const orc_sites* s, const vrt_quadrature* q, int n_sweeps, double p, double eps, int maxiter,
                          const double* alpha, const double* eps_l, const double* B0, double* S, double* J, double* conv, int hoist) {

@@ -100,3 +100,25 @@ def test_oracle_J_regular_is_the_weighted_sum_and_lambda_converges(oracle):
     ones = np.ones((n, n, n), order="F")
     Jc, Sc, conv, it = oracle.lambda_regular(ax, ax, ax, quad[:, 0], quad[:, 1], quad[:, 2], al, ones, S, eps=1e-3, maxiter=10)
     assert it == 1 and conv[0] == 1.0 and conv[1] == 0.0 and np.array_equal(Sc, S)
+
+
+def test_oracle_regular_line_J_reduces_to_the_continuum_form(oracle):
+    """with zero level populations the line opacity vanishes (line.jl:219-225), so lambda_iteration.jl:1-58 must give, per
+    wavelength, what lambda_continuum.jl:1-24 gives for α_cont with the boundary B_λ(λ, T[1,:,:]): two separately written
+    oracle routines, same numbers."""
+    import sys
+    sys.path.insert(0, HERE)
+    from regular_box import regular_line_box
+    from voronoirt_b200 import atom
+    P = regular_line_box(oracle, nz=7, nx=6, ny=7, nbb=4, nbf=2)
+    line, shape, n = P["line"], P["shape"], P["n"]
+    quad = np.loadtxt(os.path.join(HERE, "..", "voronoirt_b200", "quadratures", "ul7n12.dat"))
+    oq = oracle.make_quadrature(quad[:, 0], quad[:, 1], quad[:, 2])
+    T = P["flat"]["temperature"]
+    S = atom.B_λ(line.λ[:, None], T[None, :]).T * 0.7                                   # (n, nλ)
+    J, damping = oracle.J_lambda_regular(P["z"], P["x"], P["y"], line.as_struct(), line.λ, P["sd"], oq, S, np.zeros((3, n)))
+    a3 = P["α_cont"].reshape(shape, order="F")
+    for l in (0, len(line.λ) // 2, len(line.λ) - 1):
+        I0 = atom.B_λ(line.λ[l], P["fields"]["temperature"][0])
+        Jc = oracle.J_regular(P["z"], P["x"], P["y"], quad[:, 0], quad[:, 1], quad[:, 2], S[:, l].reshape(shape, order="F"), a3, I0)
+        assert np.abs(Jc.ravel(order="F") - J[:, l]).max() <= 1e-14 * np.abs(J[:, l]).max()

@@ -216,14 +216,45 @@ def Delaunay_downII(k, S, I_0, α, sites, n_sweeps, p=7.0):
 
 
 # ------------------------------------------------------------------ characteristics.jl (regular grid)
+class _RegularGrid:
+    """owner of a vrt_grid handle over a regular atmosphere (vrt_regular_grid_create)"""
+
+    def __init__(self, z, x, y):
+        h = C.c_void_p()
+        check(lib().vrt_regular_grid_create(len(z), len(x), len(y), _ptr(z), _ptr(x), _ptr(y), C.byref(h)))
+        self.h = h
+        self.n = len(z) * len(x) * len(y)
+        self.solvers = {}
+
+    def __del__(self):
+        try:
+            for s in self.solvers.values():
+                s.close()
+            if self.h:
+                lib().vrt_grid_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+
 class Atmosphere:
-    """src/atmosphere.jl:22-31 (same field names and order); x and y carry the periodic ghost columns."""
+    """src/atmosphere.jl:22-31 (same field names and order); x and y carry the periodic ghost columns.  The 3-D fields are
+    (nz, nx, ny) arrays; their column-major memory is the per-cell vector the C ABI takes."""
 
     def __init__(self, z, x, y, temperature=None, electron_density=None, hydrogen_populations=None,
                  velocity_z=None, velocity_x=None, velocity_y=None):
         self.z, self.x, self.y = (np.ascontiguousarray(a, dtype=np.float64) for a in (z, x, y))
         self.temperature, self.electron_density, self.hydrogen_populations = temperature, electron_density, hydrogen_populations
         self.velocity_z, self.velocity_x, self.velocity_y = velocity_z, velocity_x, velocity_y
+        self.shape = (len(self.z), len(self.x), len(self.y))
+        self.n = self.shape[0] * self.shape[1] * self.shape[2]
+        self._g = None
+
+    @property
+    def _grid(self):
+        if self._g is None:
+            self._g = _RegularGrid(self.z, self.x, self.y)
+        return self._g
 
 
 def _short_characteristics(k, S_0, I_0, α, atmos, n_sweeps, down, return_branches=False):
@@ -493,10 +524,21 @@ def Λ_voronoi(ϵ, maxiter, sites, *args, **kw):
     return J, S, _f(kw["α_cont"])
 
 
-def J_λ_regular(S_λ, α_cont, atmos, quadrature, I_0=None, I_0_down=None, n_sweeps=3):
-    """src/lambda_continuum.jl:1-24 (and lambda_iteration.jl:23-55 for a direction-independent α).  S_λ, α_cont:
+def J_λ_regular(S_λ, α_cont, *args, I_0=None, I_0_down=None, n_sweeps=3):
+    """Line form (src/lambda_iteration.jl:1-58): J_λ_regular(S_λ, α_cont, populations, atmos, line, quadrature) ->
+    (J_λ, damping_λ), S_λ (nλ, nz, nx, ny), populations (nz, nx, ny, 3); the bottom boundary is B_λ(λ, T[1,:,:]) (:38).
+    Continuum form (src/lambda_continuum.jl:1-24): J_λ_regular(S_λ, α_cont, atmos, quadrature, I_0=…).  S_λ, α_cont:
     (nz, nx, ny) or (nλ, nz, nx, ny); I_0: the bottom boundary the reference builds at :16, blackbody_λ(500 nm,
     T[1,:,:]), (nx, ny) or (nλ, nx, ny); rays with θ < 90 start from zero (:19) unless I_0_down is given."""
+    if len(args) == 4:
+        populations, atmos, line, quadrature = args
+        s = _line_solver(atmos, line, quadrature, α_cont=α_cont)
+        s.set_field("alpha_cont", α_cont)
+        shape = (s.nlam,) + atmos.shape
+        damping = np.zeros(shape, order="F")
+        J = s.mean_intensity(S_λ, populations, J=np.zeros(shape, order="F"), damping=damping)
+        return J, damping
+    atmos, quadrature = args
     nz, nx, ny = len(atmos.z), len(atmos.x), len(atmos.y)
     S_λ, α_cont = _f(S_λ), _f(α_cont)
     nlam = 1 if S_λ.ndim == 3 else S_λ.shape[0]
@@ -518,9 +560,29 @@ def J_λ_regular(S_λ, α_cont, atmos, quadrature, I_0=None, I_0_down=None, n_sw
     return J
 
 
-def Λ_regular(ϵ, maxiter, atmos, quadrature, α_cont, ε_λ, B_0, n_sweeps=3, callback=None):
-    """src/lambda_continuum.jl:58-107 -> (J, S, α_cont).  α_cont, ε_λ, B_0 (nz, nx, ny) are what the reference computes with
-    Transparency.jl at :66-85 before its loop."""
+def Λ_regular(ϵ, maxiter, atmos, *args, n_sweeps=3, callback=None, **kw):
+    """Line form (src/lambda_iteration.jl:116-205): Λ_regular(ϵ, maxiter, atmos, line, quadrature, DATA=None; α_cont, ελ, C,
+    LTE_pops) -> (J, S, α_cont, populations) with J, S (nλ, nz, nx, ny) and populations (nz, nx, ny, 3); the keyword arrays
+    are what the reference computes with Transparency.jl before its loop (:123-155).
+    Continuum form (src/lambda_continuum.jl:58-107): Λ_regular(ϵ, maxiter, atmos, quadrature, α_cont, ε_λ, B_0) ->
+    (J, S, α_cont); α_cont, ε_λ, B_0 (nz, nx, ny) as computed at :66-85."""
+    if len(args) >= 2 and not isinstance(args[0], (str, bytes, tuple, list)):
+        line, quadrature = args[0], args[1]
+        s = Solver(atmos, quadrature, line=line, α_cont=kw["α_cont"], ελ=kw["ελ"], C_rates=kw["C"], LTE_pops=kw["LTE_pops"],
+                   n_sweeps=n_sweeps, **{k: v for k, v in kw.items() if k in ("lam_chunk",)})
+        try:
+            res = s.iterate(ϵ, maxiter, callback)
+            S, J, pops = s.get_state()
+        finally:
+            s.close()
+        Λ_regular.last = res
+        shape = (s.nlam,) + atmos.shape
+        return (J.reshape(shape, order="F"), S.reshape(shape, order="F"), _f(kw["α_cont"]),
+                pops.reshape(atmos.shape + (3,), order="F"))
+    quadrature = args[0]
+    α_cont = args[1] if len(args) > 1 else kw["α_cont"]
+    ε_λ = args[2] if len(args) > 2 else kw["ε_λ"]
+    B_0 = args[3] if len(args) > 3 else kw["B_0"]
     nz, nx, ny = len(atmos.z), len(atmos.x), len(atmos.y)
     α_cont, ε_λ, B_0 = _f(α_cont), _f(ε_λ), _f(B_0)
     for a in (α_cont, ε_λ, B_0):

@@ -419,12 +419,20 @@ int vrt_grid_size(const vrt_grid* g, int64_t* n, int64_t* max_nb) {
 }
 
 int vrt_grid_num_layers(const vrt_grid* g, int32_t down, int64_t* L) {
+    if (g && g->regular) {
+        set_error("vrt_grid_num_layers: not defined on a regular grid handle");
+        return VRT_E_STATE;
+    }
     if (!g || !L) return VRT_E_INVALID;
     *L = down ? g->L_down : g->L_up;
     return VRT_OK;
 }
 
 int vrt_grid_get_layers(const vrt_grid* g, int32_t down, int64_t* perm, int64_t* offsets) {
+    if (g && g->regular) {
+        set_error("vrt_grid_get_layers: not defined on a regular grid handle");
+        return VRT_E_STATE;
+    }
     if (!g) return VRT_E_INVALID;
     const auto& p = down ? g->perm_down : g->perm_up;
     const auto& o = down ? g->off_down : g->off_up;
@@ -434,6 +442,10 @@ int vrt_grid_get_layers(const vrt_grid* g, int32_t down, int64_t* perm, int64_t*
 }
 
 int vrt_grid_get_delaunay_lines(const vrt_grid* g, double* lines) {
+    if (g && g->regular) {
+        set_error("vrt_grid_get_delaunay_lines: not defined on a regular grid handle");
+        return VRT_E_STATE;
+    }
     if (!g || !lines) return VRT_E_INVALID;
     size_t cnt = (size_t)3 * g->max_nb * g->n;
     DevBuf<double> tmp;
@@ -452,6 +464,10 @@ int vrt_grid_get_delaunay_lines(const vrt_grid* g, double* lines) {
 }
 
 int vrt_grid_get_stencil(vrt_grid* g, const double k[3], double p, int64_t* upwind, double* dots, double* weights, double* r) {
+    if (g && g->regular) {
+        set_error("vrt_grid_get_stencil: not defined on a regular grid handle");
+        return VRT_E_STATE;
+    }
     if (!g || !k) return VRT_E_INVALID;
     Stencil st;
     VRT_TRY(grid_stencil(g, k, p, &st));
@@ -476,6 +492,10 @@ int vrt_grid_get_stencil(vrt_grid* g, const double k[3], double p, int64_t* upwi
 
 int vrt_grid_get_schedule(vrt_grid* g, const double k[3], int32_t down, int32_t n_sweeps, int32_t prune,
                           int32_t* cls, int32_t* sublevel, int32_t* stab, int64_t* n_steps, int64_t* n_visits) {
+    if (g && g->regular) {
+        set_error("vrt_grid_get_schedule: not defined on a regular grid handle");
+        return VRT_E_STATE;
+    }
     if (!g || !k) return VRT_E_INVALID;
     int rc = VRT_OK;
     DirSchedule* sch = schedule_get(g, k, down, n_sweeps, 7.0, prune, 1, &rc);

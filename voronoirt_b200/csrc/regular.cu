@@ -641,10 +641,115 @@ int reg_read_diff(RegWorkspace& W, double* diff) {
     return VRT_OK;
 }
 
+
+int reg_geom_of(const vrt_grid* g, RegGeom* G) {
+    if (!g || !g->regular) {
+        set_error("internal: not a regular grid");
+        return VRT_E_STATE;
+    }
+    G->nz = g->rnz; G->nx = g->rnx; G->ny = g->rny;
+    G->plane = (size_t)g->rnx * g->rny;
+    G->vol = G->plane * g->rnz;
+    G->hz = g->rz; G->hx = g->rx; G->hy = g->ry;
+    return VRT_OK;
+}
+
 }  // namespace
+
+int regular_plan_chunk(const vrt_grid* g, int64_t nlam, double extra_vols, int64_t* lc) {
+    RegGeom G;
+    VRT_TRY(reg_geom_of(g, &G));
+    std::lock_guard<std::mutex> lock(g_reg_mu);
+    RegWorkspace* Wp = nullptr;
+    VRT_TRY(reg_workspace(&Wp));
+    // internal: S in both layouts, alpha in both, I
+    return reg_plan_chunk("regular solver", G, *Wp, nlam, 5.0 + extra_vols, 4.0, lc);
+}
+
+int regular_dir_accumulate(const vrt_grid* g, const double k[3], int down, int n_sweeps, int64_t n_l, const double* S, int64_t S_ld,
+                           int64_t S_l0, const double* alpha, int64_t a_ld, int64_t a_l0, const double* I0, double* J, int64_t J_ld,
+                           int64_t J_l0, double w, int accumulate, bool have_S[2], SweepStats* st) {
+    const char* who = "regular solver";
+    RegGeom G;
+    VRT_TRY(reg_geom_of(g, &G));
+    RegDir D;
+    VRT_TRY(reg_dir_setup(who, G, k, down, &D));
+    const int lay = D.P.par_is_x;
+    std::lock_guard<std::mutex> lock(g_reg_mu);
+    RegWorkspace* Wp = nullptr;
+    VRT_TRY(reg_workspace(&Wp));
+    RegWorkspace& W = *Wp;
+    const size_t need_vol = G.vol * n_l;
+    if (W.dI.n < need_vol || (W.dS[lay].p && W.dS[lay].n < need_vol) || (W.dA[lay].p && W.dA[lay].n < need_vol)) {
+        W.release_arrays();
+        have_S[0] = have_S[1] = false;
+    }
+    if (!W.dS[lay].p) have_S[lay] = false;
+    VRT_TRY(W.dI.ensure(need_vol));
+    VRT_TRY(W.dS[lay].ensure(need_vol));
+    VRT_TRY(W.dA[lay].ensure(need_vol));
+    VRT_TRY(reg_common_buffers(G, W, n_l));
+    if (!have_S[lay]) {
+        VRT_TRY(reg_load(G, S, true, G.nz, S_ld, S_l0, n_l, lay, W.dS[lay].p, W.stage, st));
+        have_S[lay] = true;
+    }
+    VRT_TRY(reg_load(G, alpha, true, G.nz, a_ld, a_l0, n_l, lay, W.dA[lay].p, W.stage, st));
+    double* pl = W.dI.p + G.plane * n_l * (down ? G.nz - 1 : 0);
+    if (I0) VRT_TRY(reg_load(G, I0, true, 1, n_l, 0, n_l, lay, pl, W.stage0, st));
+    else VRT_CUDA(cudaMemsetAsync(pl, 0, sizeof(double) * G.plane * n_l));
+    EvPair ev;
+    VRT_TRY(ev.create());
+    VRT_CUDA(cudaEventRecord(ev.a));
+    VRT_TRY(reg_plane_loop(G, W, D, n_sweeps, n_l, W.dS[lay].p, W.dA[lay].p, W.dI.p, st, nullptr));
+    VRT_CUDA(cudaEventRecord(ev.b));
+    VRT_TRY(reg_store(G, W.dI.p, J, true, J_ld, J_l0, n_l, lay, w, accumulate, W.stage, st));
+    VRT_CUDA(cudaDeviceSynchronize());
+    float ms = 0;
+    VRT_CUDA(cudaEventElapsedTime(&ms, ev.a, ev.b));
+    st->sweep_ms += ms;
+    st->visits += (double)(G.nz - 1) * (double)(G.nx - 2) * (double)(G.ny - 2) * (double)n_l;
+    return VRT_OK;
+}
+
 }  // namespace vrt
 
 using namespace vrt;
+
+/* a vrt_grid over the regular Cartesian atmosphere: cell c = iz + nz*(ix + nx*iy), the memory order of the reference's
+ * (nz, nx, ny) arrays */
+extern "C" int vrt_regular_grid_create(int64_t nz, int64_t nx, int64_t ny, const double* z, const double* x, const double* y,
+                                       vrt_grid** out) {
+    if (!out) return VRT_E_INVALID;
+    *out = nullptr;
+    RegGeom G;
+    VRT_TRY(reg_check_geom("vrt_regular_grid_create", nz, nx, ny, z, x, y, &G));
+    if (G.vol >= ((size_t)1 << 31)) {
+        set_error("vrt_regular_grid_create: more than 2^31 cells");
+        return VRT_E_INVALID;
+    }
+    vrt_grid* g = new vrt_grid();
+    struct Guard { vrt_grid* g; ~Guard() { delete g; } } guard{g};
+    g->regular = true;
+    g->n = (int64_t)G.vol;
+    g->rnz = nz; g->rnx = nx; g->rny = ny;
+    g->rz = G.hz; g->rx = G.hx; g->ry = G.hy;
+    g->bounds[0] = G.hz.front(); g->bounds[1] = G.hz.back();
+    g->bounds[2] = G.hx.front(); g->bounds[3] = G.hx.back();
+    g->bounds[4] = G.hy.front(); g->bounds[5] = G.hy.back();
+    VRT_CUDA(cudaGetDevice(&g->device));
+    // identity maps: the generic host<->internal copies of solver.cu then work unchanged
+    std::vector<int32_t> id((size_t)g->n);
+    for (int64_t i = 0; i < g->n; i++) id[(size_t)i] = (int32_t)i;
+    VRT_TRY(g->site_of.alloc((size_t)g->n));
+    VRT_TRY(g->rank_of.alloc((size_t)g->n));
+    VRT_CUDA(cudaMemcpy(g->site_of.p, id.data(), sizeof(int32_t) * id.size(), cudaMemcpyHostToDevice));
+    VRT_CUDA(cudaMemcpy(g->rank_of.p, id.data(), sizeof(int32_t) * id.size(), cudaMemcpyHostToDevice));
+    g->off_up = {1, 1};
+    g->off_down = {1, 1};
+    guard.g = nullptr;
+    *out = g;
+    return VRT_OK;
+}
 
 extern "C" int vrt_regular_formal_solve(int64_t nz, int64_t nx, int64_t ny, const double* z, const double* x, const double* y,
                                         const double k[3], int32_t down, int32_t n_sweeps, int64_t nlam, const double* S,

@@ -276,6 +276,17 @@ int continuum_source_update(int64_t n, const double* B0, const double* eps, cons
     return VRT_OK;
 }
 
+// bottom boundary of the regular grid: I_0 = B_λ.(λ, T[1,:,:]) (lambda_iteration.jl:38) or B_0[1,:,:] (lambda_continuum.jl:16);
+// out is [nx*ny][lc], cell (iz = 0, i) of the (nz, nx, ny) arrays is nz*i
+__global__ void k_regular_boundary(double* __restrict__ out, int64_t lc, const double* __restrict__ lam, const double* __restrict__ T,
+                                   const double* __restrict__ B0, int64_t nz, int64_t plane) {
+    int64_t total = plane * lc;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t c = i / lc, l = i - c * lc;
+        out[i] = B0 ? B0[nz * c] : B_lambda(lam[l], T[nz * c]);
+    }
+}
+
 __global__ void k_planck_rows(int64_t n, int64_t nlam, const double* __restrict__ lam, const double* __restrict__ T, double* __restrict__ S) {
     int64_t total = n * nlam;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -543,8 +554,11 @@ static int solver_common_init(vrt_solver* s, vrt_grid* g, const vrt_quadrature* 
         std::array<double, 3> k = {cos(t * PI / 180), cos(p * PI / 180) * sin(t * PI / 180), sin(p * PI / 180) * sin(t * PI / 180)};
         int down = !(t > 90);
         int rc = VRT_OK;
-        DirSchedule* sc = schedule_get(g, k.data(), down, c.n_sweeps, c.p, c.prune, cv, &rc);
-        if (!sc) return rc;
+        DirSchedule* sc = nullptr;
+        if (!g->regular) {
+            sc = schedule_get(g, k.data(), down, c.n_sweeps, c.p, c.prune, cv, &rc);
+            if (!sc) return rc;
+        }
         s->qk.push_back(k);
         s->qw.push_back(w[i]);
         s->qdown.push_back(down);
@@ -553,6 +567,10 @@ static int solver_common_init(vrt_solver* s, vrt_grid* g, const vrt_quadrature* 
     s->nd = (int)s->qk.size();
     s->n1_up = g->off_up[1] - 1;
     s->n1_dn = g->off_down[1] - 1;
+    if (g->regular && (s->cell_R > 1 || s->dir_sharded)) {
+        set_error("solver: direction / cell shards are not implemented on the regular grid");
+        return VRT_E_INVALID;
+    }
     VRT_TRY(s->diff_bits.alloc(1));
     VRT_TRY(s->diff_nan.alloc(1));
     return VRT_OK;
@@ -571,6 +589,30 @@ static int upload_site_vec(const vrt_grid* g, const double* src, DevBuf<double>&
 static int plan_buffers(vrt_solver* s) {
     if (s->lc > 0) return VRT_OK;
     const int64_t n = s->n;
+    if (s->g->regular) {
+        // per wavelength: alpha_tot in the caller's layout (line only) next to regular.cu's five internal volumes
+        int64_t lc = 0;
+        VRT_TRY(regular_plan_chunk(s->g, s->nlam, s->is_line ? 1.0 : 0.0, &lc));
+        if (s->cfg.lam_chunk > 0) lc = std::min<int64_t>(lc, s->cfg.lam_chunk);
+        const int64_t passes = (s->nlam + lc - 1) / lc;
+        lc = (s->nlam + passes - 1) / passes;
+        s->lc = lc;
+        s->db = 1;
+        s->alpha_p.assign(1, nullptr);
+        s->I_p.assign(1, nullptr);
+        s->scr_p.assign(1, std::array<double*, MAX_SWEEPS>{});
+        auto* b0 = new DevBuf<double>();   // boundary plane [nx*ny][lc]
+        s->bufs.push_back(b0);
+        VRT_TRY(b0->alloc((size_t)(s->g->rnx * s->g->rny) * lc));
+        s->I_p[0] = b0->p;
+        if (s->is_line) {
+            auto* ba = new DevBuf<double>();
+            s->bufs.push_back(ba);
+            VRT_TRY(ba->alloc((size_t)n * lc + 2));
+            s->alpha_p[0] = ba->p;
+        }
+        return VRT_OK;
+    }
     size_t free_b = 0, total_b = 0;
     VRT_CUDA(cudaMemGetInfo(&free_b, &total_b));
     double budget = 0.85 * (double)free_b;
@@ -651,6 +693,58 @@ static int mean_intensity_internal(vrt_solver* s, SweepStats* stats, double* t_o
         k_gamma<<<nblocks(n, 256), 256>>>(n, s->ld, s->T.p, s->ne.p, s->pops.p, s->gamma.p);
         s->gamma_valid = true;
         stats->kernels += 1;
+    }
+    if (s->g->regular) {
+        // J_λ_regular (lambda_iteration.jl:1-58 / lambda_continuum.jl:1-24): directions one after the other, per direction
+        // alpha_tot (:32-35), the bottom boundary B_λ(T[1,:,:]) for θ > 90 (:38) or zero (:46), the plane walk, J += w I
+        const int64_t plane = s->g->rnx * s->g->rny;
+        for (int64_t l0 = 0; l0 < s->nlam; l0 += s->lc) {
+            const int64_t lc = std::min(s->lc, s->nlam - l0);
+            bool have_S[2] = {false, false};
+            for (int d = 0; d < s->nd; d++) {
+                const double* alpha = s->alpha_cont.p;
+                int64_t a_ld = 1;
+                if (s->is_line) {
+                    OpacityDirs od;
+                    od.nd = 1;
+                    for (int a = 0; a < 3; a++) od.k[0][a] = s->qk[d][a];
+                    od.alpha[0] = s->alpha_p[0];
+                    VRT_CUDA(cudaEventRecord(e0));
+                    const size_t shm = sizeof(double) * OP_TC * (size_t)((int)lc | 1);
+                    const int grid = (int)std::min<int64_t>((n + OP_TC - 1) / OP_TC, 148 * 16);
+                    if (shm > 48 * 1024) VRT_CUDA(cudaFuncSetAttribute(k_opacity, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
+                    k_opacity<<<grid, OP_THREADS, shm>>>(n, lc, s->lam_dev.p + s->l_begin + l0, s->ld, od, s->gamma.p, s->dD.p, s->vz.p,
+                                                        s->vx.p, s->vy.p, s->pops.p, s->alpha_cont.p);
+                    VRT_CUDA(cudaEventRecord(e1));
+                    VRT_CUDA(cudaGetLastError());
+                    stats->kernels += 1;
+                    alpha = s->alpha_p[0];
+                    a_ld = lc;
+                }
+                const double* I0 = nullptr;
+                if (!s->qdown[d]) {
+                    k_regular_boundary<<<nblocks(plane * lc, 256), 256>>>(s->I_p[0], lc, s->lam_dev.p + s->l_begin + l0, s->T.p,
+                                                                         s->is_line ? nullptr : s->B0.p, s->g->rnz, plane);
+                    VRT_CUDA(cudaGetLastError());
+                    stats->kernels += 1;
+                    I0 = s->I_p[0];
+                }
+                VRT_TRY(regular_dir_accumulate(s->g, s->qk[d].data(), s->qdown[d], s->cfg.n_sweeps, lc, s->S.p, s->nlam, l0, alpha, a_ld, 0,
+                                               I0, s->J.p, s->nlam, l0, s->qw[d], d > 0, have_S, stats));
+                if (s->is_line) {
+                    float ms = 0;
+                    VRT_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+                    opacity_ms += ms;
+                }
+            }
+        }
+        if (s->nd == 0) VRT_CUDA(cudaMemset(s->J.p, 0, sizeof(double) * (size_t)n * s->nlam));
+        VRT_CUDA(cudaDeviceSynchronize());
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+        if (t_opacity_ms) *t_opacity_ms = opacity_ms;
+        if (t_sweep_ms) *t_sweep_ms = stats->sweep_ms;
+        return VRT_OK;
     }
     for (int64_t l0 = 0; l0 < s->nlam; l0 += s->lc) {
         int64_t lc = std::min(s->lc, s->nlam - l0);
@@ -843,6 +937,10 @@ int vrt_formal_solve(vrt_grid* g, const double k[3], int32_t down, double p, int
     if (!g || !k || !S || !alpha || !I_out || nlam <= 0) {
         set_error("vrt_formal_solve: bad arguments");
         return VRT_E_INVALID;
+    }
+    if (g->regular) {
+        set_error("vrt_formal_solve: regular grid handle — use vrt_regular_formal_solve");
+        return VRT_E_STATE;
     }
     const int64_t n = g->n;
     int rc = VRT_OK;

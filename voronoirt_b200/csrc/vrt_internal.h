@@ -144,6 +144,11 @@ struct vrt_grid {
     // ready-flags of the dataflow sweep: flag == epoch <=> chunk done in the current launch (no memset per launch)
     vrt::DevBuf<int32_t> flag_pool;
     int32_t epoch = 0;
+    // regular Cartesian grid (vrt_regular_grid_create): cells in the Julia (nz, nx, ny) order, identity permutation,
+    // no layers / stencils / schedules; the formal solver is regular.cu's plane walk
+    bool regular = false;
+    int64_t rnz = 0, rnx = 0, rny = 0;
+    std::vector<double> rz, rx, ry;
     ~vrt_grid();
 };
 
@@ -176,6 +181,14 @@ int sweep_scratch_rows(const DirSchedule* sch, int s);
 // misc kernels (physics.cu)
 int permute_rows(const double* src, double* dst, const int32_t* map, int64_t n, int64_t nlam, int gather, cudaStream_t st);
 extern thread_local SweepStats g_last_stats;
+// regular.cu: one direction of J_λ_regular on DEVICE arrays in the caller's [cell][λ] layout (ld = wavelengths per cell,
+// l0 = first wavelength of the chunk): J[.., l0:l0+n_l] (+)= w * I.  I0: [nx*ny][n_l] boundary plane or nullptr (zero).
+// have_S[layout] says whether S of this chunk is already laid out (cleared by the caller per chunk / per new S).
+int regular_dir_accumulate(const vrt_grid* g, const double k[3], int down, int n_sweeps, int64_t n_l, const double* S, int64_t S_ld,
+                           int64_t S_l0, const double* alpha, int64_t a_ld, int64_t a_l0, const double* I0, double* J, int64_t J_ld,
+                           int64_t J_l0, double w, int accumulate, bool have_S[2], SweepStats* st);
+// wavelengths per chunk that fit next to `extra_vols` more volumes per wavelength held by the caller
+int regular_plan_chunk(const vrt_grid* g, int64_t nlam, double extra_vols, int64_t* lc);
 // S_new = (1-ε)J + εB with the criterion fused / the criterion alone, one wavelength (solver.cu; used by regular.cu)
 int continuum_criterion(int64_t n, const double* S_new, const double* S_old, const double* eps, unsigned long long* diff_bits, int* diff_nan);
 int continuum_source_update(int64_t n, const double* B0, const double* eps, const double* J, double* S, unsigned long long* diff_bits,
