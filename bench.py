@@ -37,6 +37,8 @@ WORKLOADS = {
     "nlte_1m_direct": (1000000, 1, 1, "ul7n12", 50, 20),   # 1 M sites tessellated directly (no tiling): slower set-up, same solve
     "nlte_4m": (250000, 4, 4, "ul9n20", 50, 20),
     "nlte_16m": (250000, 8, 8, "ul9n20", 50, 20),
+    # BASELINE configs[3]: the regular-grid comparison solver, 256 x 256 x 400 (+ ghost columns), ul7n12, 91 wavelengths (N = 1 only)
+    "regular_400": (0, 1, 1, "ul7n12", 50, 20),
 }
 
 
@@ -193,6 +195,8 @@ def main():
     W = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 0)
     K = max(args.steps, 1)
 
+    if args.workload.startswith("regular"):
+        return main_regular(args, W, K)
     if args.impl == "reference":
         if rank != 0:
             return 0
@@ -420,6 +424,169 @@ def main():
     solver.close()
     if dist is not None:
         dist.destroy_process_group()
+    return 0
+
+
+def regular_problem(nz, nx, ny, nbb, nbf):
+    """Synthetic Bifrost-shaped atmosphere on the regular grid of BASELINE configs[3]: x, y uniform with periodic ghost
+    columns, z stretched from 12 km to 60 km spacing.  -> axes, (nz, nx, ny) fields (column-major), line inputs."""
+    from voronoirt_b200 import synth
+    B = synth.BOX
+    n_fine = (3 * nz) // 4
+    dz = np.concatenate([np.full(n_fine, 12e3), np.linspace(12e3, 60e3, nz - 1 - n_fine)])
+    z = np.concatenate([[B["z_min"]], B["z_min"] + np.cumsum(dz)])
+    x = (np.arange(nx) - 1) * (B["x_max"] / (nx - 2))
+    y = (np.arange(ny) - 1) * (B["y_max"] / (ny - 2))
+    fields = {}
+    # evaluate plane by plane in y to bound the temporaries; the atmosphere is periodic in x and y
+    Zp, Xp = np.meshgrid(z, np.mod(x, B["x_max"]), indexing="ij")
+    cols = {k: [] for k in ("temperature", "electron_density", "hydrogen_density", "velocity_z", "velocity_x", "velocity_y")}
+    for iy in range(ny):
+        a = synth.atmosphere(Zp.ravel(order="F"), Xp.ravel(order="F"), np.full(Zp.size, np.mod(y[iy], B["y_max"])))
+        for k in cols:
+            cols[k].append(np.asarray(a[k], dtype=np.float64))
+    flat = {k: np.concatenate(v) for k, v in cols.items()}           # cell = iz + nz*(ix + nx*iy)
+    for k, v in flat.items():
+        f = v.reshape((nz, nx, ny), order="F")
+        f[:, 0, :] = f[:, -2, :]; f[:, -1, :] = f[:, 1, :]
+        f[:, :, 0] = f[:, :, -2]; f[:, :, -1] = f[:, :, 1]
+        fields[k] = f
+    line, lte, α_cont, ελ, Cr = synth.line_inputs(flat["temperature"], flat["electron_density"], flat["hydrogen_density"], nbb, nbf)
+    return dict(z=z, x=x, y=y, shape=(nz, nx, ny), n=nz * nx * ny, fields=fields, flat=flat, line=line, lte=lte, α_cont=α_cont, ελ=ελ, C=Cr)
+
+
+def main_regular(args, W, K):
+    """BASELINE configs[3]: NLTE line Λ-iteration on the regular grid (Λ_regular, lambda_iteration.jl:116-205), one GPU."""
+    rank = int(os.environ.get("RANK", "0"))
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        if rank == 0:
+            print(json.dumps({"workload": args.workload, "unavailable": "the regular-grid path is single-GPU this round (replicas only)"}))
+        return 0
+    base, kx, ky, qname, nbb, nbf = WORKLOADS[args.workload]
+    shape = tuple(int(v) for v in os.environ.get("VRT_REG_SHAPE", "400,258,258").split(","))
+    from voronoirt_b200 import api
+    qpath = api.quadrature_path(qname)
+    w, th, ph, nq = api.read_quadrature(qpath)
+    ndirs = int(np.sum(th != 90))
+    metric = "cell*angle*freq updates/s per formal solution (NLTE Lambda-iteration)"
+
+    def cpu_sample(threads):
+        """the oracle's J_λ_regular (port of lambda_iteration.jl:1-58, threads over wavelengths like :30) on a narrower box of the
+        same atmosphere: all wavelengths x one direction per ray routine (yz, xy, xz)"""
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import oracle as O
+        from voronoirt_b200 import atom
+        nzs, nxs, nys = shape[0], min(shape[1], 66), min(shape[2], 66)
+        Q = regular_problem(nzs, nxs, nys, nbb, nbf)
+        line = Q["line"]
+        sd = O.make_site_data(temperature=Q["flat"]["temperature"], electron_density=Q["flat"]["electron_density"],
+                              hydrogen_density=Q["flat"]["hydrogen_density"], velocity_z=Q["flat"]["velocity_z"],
+                              velocity_x=Q["flat"]["velocity_x"], velocity_y=Q["flat"]["velocity_y"], doppler_width=line.ΔD,
+                              alpha_cont=Q["α_cont"], destruction=Q["ελ"], C=np.ascontiguousarray(Q["C"].T), lte_pops=np.ascontiguousarray(Q["lte"].T))
+        pick = [0, 2, 8] if nq >= 9 else [0]
+        oq = O.make_quadrature(w[pick], th[pick], ph[pick])
+        S = np.ascontiguousarray(atom.B_λ(line.λ[None, :], Q["flat"]["temperature"][:, None]))
+
+        def run():
+            t = time.perf_counter()
+            O.J_lambda_regular(Q["z"], Q["x"], Q["y"], line.as_struct(), line.λ, sd, oq, S, Q["lte"].T)
+            return time.perf_counter() - t
+        upd = float(nzs - 1) * (nxs - 2) * (nys - 2) * len(line.λ) * len(pick)
+        sample = (f"all {len(line.λ)} wavelengths x {len(pick)} of {ndirs} directions (one per ray routine) on a {nzs} x {nxs} x {nys} box of the same "
+                  "atmosphere; C/OpenMP port of J_λ_regular (Julia not installed)")
+        return run, upd, sample, O.num_threads()
+
+    if args.impl == "reference":
+        run, upd, sample, threads = cpu_sample(os.cpu_count() or 1)
+        for _ in range(min(W, 1)):
+            run()
+        t = float(np.mean([run() for _ in range(K)]))
+        val = upd / t
+        print(json.dumps({"impl": "reference", "metric": metric, "value": val, "unit": "updates/s", "n_gpus": args.gpus, "steps": K,
+                          "warmup": min(W, 1), "ms_per_step": 1e3 * t, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                          "dtype": "f64", "data": "synthetic", "config": {"workload": f"{args.workload}: regular grid {shape}, {qname}"},
+                          "cpu_baseline": {"value": val, "unit": "updates/s", "cores": threads, "kind": "port", "sample": sample},
+                          "e2e": {"value": val, "unit": "updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return 0
+
+    import torch
+    import voronoirt_b200 as V
+    from voronoirt_b200 import _lib
+    torch.cuda.set_device(0)
+    t_setup = time.time()
+    Q = regular_problem(*shape, nbb, nbf)
+    line, n, f = Q["line"], Q["n"], Q["fields"]
+    nlam = len(line.λ)
+    atm = V.Atmosphere(Q["z"], Q["x"], Q["y"], f["temperature"], f["electron_density"], f["hydrogen_density"], f["velocity_z"],
+                       f["velocity_x"], f["velocity_y"])
+    # two wavelength chunks: leaves room for the host<->device staging buffer of the e2e leg next to S, J and the workspace
+    lam_chunk = int(os.environ.get("VRT_REG_BENCH_CHUNK", str((nlam + 1) // 2 if n * nlam * 8 > 8e9 else 0)))
+    solver = V.Solver(atm, qpath, line=line, α_cont=Q["α_cont"], ελ=Q["ελ"], C_rates=Q["C"], LTE_pops=Q["lte"], lam_chunk=lam_chunk)
+    log(f"setup {time.time() - t_setup:.1f}s: regular grid {shape} = {n} cells, dirs={ndirs} nlam={nlam}")
+    solver.iterate(-1.0, W)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(0)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    res = solver.iterate(-1.0, K)
+    e1.record()
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    ms = e0.elapsed_time(e1)
+    stats = _lib.last_stats()
+    hist = res["history"]
+    interior = float(shape[0] - 1) * (shape[1] - 2) * (shape[2] - 2)
+    updates = interior * ndirs * nlam
+    value = updates / (ms / K / 1e3)
+    B_alg = 40.0            # S read 8, alpha read 8, I write 8, J read-modify-write 16 per (cell, direction, wavelength)
+    achieved = B_alg * updates * K / (stats["sweep_ms"] / 1e3) / 1e9 if stats["sweep_ms"] > 0 else 0.0
+    peak, peak_src = measured_peak()
+    roofline = {"bound": "hbm", "kernel": "regular plane walk (k_reg_xy | k_reg_coef + k_reg_rec)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_update": B_alg,
+                "sweep_ms_per_step": stats["sweep_ms"] / K, "sweep_share_of_step": stats["sweep_ms"] / ms,
+                "note": "k_reg_rec is latency-bound (one CTA per wavelength), see DESIGN.md 5b"}
+    e2e = None
+    if not args.no_e2e:
+        try:
+            import ctypes as C
+            L = _lib.lib()
+            hS = torch.empty((n, nlam), dtype=torch.float64).pin_memory()
+            hP = torch.empty((3, n), dtype=torch.float64).pin_memory()
+            _lib.check(L.vrt_get_state(solver.h, C.c_void_p(hS.data_ptr()), None, C.c_void_p(hP.data_ptr())))
+            null_cb = _abi_null_cb()
+
+            def step():
+                _lib.check(L.vrt_set_state(solver.h, C.c_void_p(hS.data_ptr()), C.c_void_p(hP.data_ptr())))
+                _lib.check(L.vrt_lambda_iterate(solver.h, -1.0, 1, null_cb, None, None))
+                _lib.check(L.vrt_get_state(solver.h, C.c_void_p(hS.data_ptr()), None, C.c_void_p(hP.data_ptr())))
+            step()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(K):
+                step()
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            e2e = {"value": updates / (dt / K), "unit": "updates/s", "h2d_bytes_per_step": int(8 * (n * nlam + 3 * n)),
+                   "d2h_bytes_per_step": int(8 * (n * nlam + 3 * n)), "ms_per_step": 1e3 * dt / K,
+                   "api": "vrt_set_state(S, populations) + vrt_lambda_iterate(1 iteration) + vrt_get_state(S, populations) on a regular-grid handle, pinned host buffers"}
+        except Exception as ex:
+            log(f"e2e leg failed: {ex}")
+    cpu = None
+    if not args.no_cpu_baseline:
+        run, upd, sample, threads = cpu_sample(os.cpu_count() or 1)
+        t = run()
+        cpu = {"value": upd / t, "unit": "updates/s", "cores": threads, "kind": "port", "sample": sample + f" ({t:.1f} s)"}
+    print(json.dumps({"metric": metric, "value": value, "unit": "updates/s", "n_gpus": 1, "steps": K, "warmup": W, "ms_per_step": ms / K,
+                      "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                      "config": {"workload": f"{args.workload}: NLTE line Lambda-iteration on the regular grid {shape[0]} x {shape[1]} x {shape[2]} (ghost columns included), "
+                                             f"{qname}, {nlam} wavelengths, synthetic Bifrost-shaped atmosphere", "cells": n, "quadrature": qname,
+                                 "n_dirs": ndirs, "n_lambda": nlam, "parallelism": "single GPU",
+                                 "l2_policy": f"inputs larger than L2 (S+J+alpha = {8 * n * nlam * 3 / 1e9:.1f} GB)", "n_sweeps": 3},
+                      "s_per_lambda_iteration": ms / K / 1e3, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+                      "gpu_launches": int(max(stats["kernels"], 1)), "clocks": clocks,
+                      "stage_ms": {k: float(np.mean([h[k] for h in hist])) for k in ("t_opacity_ms", "t_sweep_ms", "t_source_ms", "t_rates_ms", "t_stateq_ms", "t_total_ms")} if hist else None}))
+    solver.close()
     return 0
 
 
