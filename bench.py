@@ -519,8 +519,7 @@ def main_regular(args, W, K):
     nlam = len(line.λ)
     atm = V.Atmosphere(Q["z"], Q["x"], Q["y"], f["temperature"], f["electron_density"], f["hydrogen_density"], f["velocity_z"],
                        f["velocity_x"], f["velocity_y"])
-    # two wavelength chunks: leaves room for the host<->device staging buffer of the e2e leg next to S, J and the workspace
-    lam_chunk = int(os.environ.get("VRT_REG_BENCH_CHUNK", str((nlam + 1) // 2 if n * nlam * 8 > 8e9 else 0)))
+    lam_chunk = int(os.environ.get("VRT_REG_BENCH_CHUNK", "0"))   # 0: as many wavelengths per pass as the free HBM allows
     solver = V.Solver(atm, qpath, line=line, α_cont=Q["α_cont"], ελ=Q["ελ"], C_rates=Q["C"], LTE_pops=Q["lte"], lam_chunk=lam_chunk)
     log(f"setup {time.time() - t_setup:.1f}s: regular grid {shape} = {n} cells, dirs={ndirs} nlam={nlam}")
     solver.iterate(-1.0, W)

@@ -55,15 +55,6 @@ __device__ __forceinline__ void reg_weights(double dtau, double& a, double& b, d
     }
 }
 
-// bilinear (functions.jl:328-355): the first coordinate selects the row of [Q11 Q12; Q21 Q22]
-__device__ __forceinline__ double reg_bilinear(double xm, double ym, double x1, double x2, double y1, double y2,
-                                               double Q11, double Q12, double Q21, double Q22) {
-    const double dx = x2 - x1, dy = y2 - y1;
-    const double f1 = ((x2 - xm) * Q11 + (xm - x1) * Q21) / dx;
-    const double f2 = ((x2 - xm) * Q12 + (xm - x1) * Q22) / dx;
-    return ((y2 - ym) * f1 + (ym - y1) * f2) / dy;
-}
-
 // ------------------------------------------------------------------ layout conversion
 // src: caller's (nlam_src, nz, nx, ny) column-major, wavelengths [l0, l0+lc) -> dst [iz][l][s][j].
 // Tile of 32 (q = l + lc*iz) x 32 (j) per block, one s per blockIdx.z; TO_INTERNAL = 0 is the inverse copy.
@@ -119,85 +110,105 @@ __global__ void k_reg_transpose(const double* __restrict__ src, double* __restri
     }
 }
 
+// bilinear (functions.jl:328-355): the first coordinate selects the row of [Q11 Q12; Q21 Q22].  The three interpolations
+// of one point (alpha, S, I) and all its wavelengths share the geometry: the corner weights are formed once per thread,
+// with the two divisions of `bilinear` as reciprocals (same operation order otherwise).
+struct RegBil {
+    double ax, bx, idx, ay, by, idy;
+    __device__ __forceinline__ RegBil(double xm, double ym, double x1, double x2, double y1, double y2)
+        : ax(x2 - xm), bx(xm - x1), idx(1.0 / (x2 - x1)), ay(y2 - ym), by(ym - y1), idy(1.0 / (y2 - y1)) {}
+    __device__ __forceinline__ double operator()(double Q11, double Q12, double Q21, double Q22) const {
+        const double f1 = (ax * Q11 + bx * Q21) * idx;
+        const double f2 = (ax * Q12 + bx * Q22) * idx;
+        return (ay * f1 + by * f2) * idy;
+    }
+};
+
+constexpr int REG_LPT = 4;   // wavelengths per thread in the plane kernels
+
 // ------------------------------------------------------------------ xy branch
-// xy_up_ray / xy_down_ray (characteristics.jl:191-280, :290-373).  One thread per (j, s, l) INCLUDING the ghost
-// columns: a ghost evaluates the interior point it mirrors (:270-279), which is the same arithmetic, so no second pass.
-// Sc/ac: plane idz; Su/au/Iu: upwind plane; cz = z[upwind] - z[idz].
-__global__ void k_reg_xy(RegPlane P, double dz, const double* __restrict__ cj, const double* __restrict__ cs,
+// xy_up_ray / xy_down_ray (characteristics.jl:191-280, :290-373).  One thread per (s, j) INCLUDING the ghost columns (a
+// ghost evaluates the interior point it mirrors (:270-279): same arithmetic, no second pass) and REG_LPT wavelengths.
+// Sc/ac: plane idz; Su/au/Iu: upwind plane; r = |dz / k_z| from the host.
+__global__ void k_reg_xy(RegPlane P, double r, const double* __restrict__ cj, const double* __restrict__ cs,
                          const double* __restrict__ Sc, const double* __restrict__ ac, const double* __restrict__ Su,
                          const double* __restrict__ au, const double* __restrict__ Iu, double* __restrict__ Iout) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;   // flattened (s, j): np need not be a multiple of the block
-    const int l = blockIdx.y;
     if (idx >= P.np * P.ns) return;
     const int s = idx / P.np, j = idx - s * P.np;
     const int gj = reg_wrap(j, P.np), gs = reg_wrap(s, P.ns);
-    const double r = fabs(dz / P.kz);
     const double jinc = r * P.kj, sinc = r * P.ks;
     const int jl = gj - (P.sgn_j + 1) / 2, ju = jl + 1;
     const int sl = gs - (P.sgn_s + 1) / 2, su = sl + 1;
     const double jup = cj[gj] + jinc, sup = cs[gs] + sinc;
     const double jb1 = cj[jl], jb2 = cj[ju], sb1 = cs[sl], sb2 = cs[su];
-    const size_t base = (size_t)l * P.np * P.ns;
-    const size_t oll = base + (size_t)sl * P.np + jl, olu = base + (size_t)su * P.np + jl;   // (j low, s low), (j low, s up)
-    const size_t oul = oll + 1, ouu = olu + 1;
-    const size_t oc = base + (size_t)gs * P.np + gj;
-    double a_u, S_u, I_u;
-    if (P.par_is_x) {   // j = x is the first coordinate of bilinear
-        a_u = reg_bilinear(jup, sup, jb1, jb2, sb1, sb2, au[oll], au[olu], au[oul], au[ouu]);
-        S_u = reg_bilinear(jup, sup, jb1, jb2, sb1, sb2, Su[oll], Su[olu], Su[oul], Su[ouu]);
-        I_u = reg_bilinear(jup, sup, jb1, jb2, sb1, sb2, Iu[oll], Iu[olu], Iu[oul], Iu[ouu]);
-    } else {            // s = x
-        a_u = reg_bilinear(sup, jup, sb1, sb2, jb1, jb2, au[oll], au[oul], au[olu], au[ouu]);
-        S_u = reg_bilinear(sup, jup, sb1, sb2, jb1, jb2, Su[oll], Su[oul], Su[olu], Su[ouu]);
-        I_u = reg_bilinear(sup, jup, sb1, sb2, jb1, jb2, Iu[oll], Iu[oul], Iu[olu], Iu[ouu]);
+    // bilinear's first coordinate is x: j when par_is_x, else s
+    const RegBil W = P.par_is_x ? RegBil(jup, sup, jb1, jb2, sb1, sb2) : RegBil(sup, jup, sb1, sb2, jb1, jb2);
+    const size_t pl = (size_t)P.np * P.ns;
+    const size_t oll = (size_t)sl * P.np + jl, olu = (size_t)su * P.np + jl;   // (j low, s low), (j low, s up)
+    // [Q11 Q12; Q21 Q22] = [x low,y low  x low,y up; x up,y low  x up,y up]
+    const size_t o11 = oll, o22 = olu + 1;
+    const size_t o12 = P.par_is_x ? olu : oll + 1, o21 = P.par_is_x ? oll + 1 : olu;
+    const size_t oc = (size_t)gs * P.np + gj, oo = (size_t)s * P.np + j;
+    const int l0 = blockIdx.y * REG_LPT, l1 = min(l0 + REG_LPT, P.lc);
+#pragma unroll
+    for (int q = 0; q < REG_LPT; q++) {
+        const int l = l0 + q;
+        if (l < l1) {
+            const size_t b = (size_t)l * pl;
+            const double a_u = W(au[b + o11], au[b + o12], au[b + o21], au[b + o22]);
+            const double S_u = W(Su[b + o11], Su[b + o12], Su[b + o21], Su[b + o22]);
+            const double I_u = W(Iu[b + o11], Iu[b + o12], Iu[b + o21], Iu[b + o22]);
+            const double dtau = r * (ac[b + oc] + a_u) / 2;
+            double wa, wb, we;
+            reg_weights(dtau, wa, wb, we);
+            Iout[b + oo] = we * I_u + wa * S_u + wb * Sc[b + oc];
+        }
     }
-    const double dtau = r * (ac[oc] + a_u) / 2;
-    double a, b, e;
-    reg_weights(dtau, a, b, e);
-    Iout[base + (size_t)s * P.np + j] = e * I_u + a * S_u + b * Sc[oc];
 }
 
 // ------------------------------------------------------------------ yz / xz branch, parallel part
 // Coefficients of the row recurrence for every interior point of plane idz (yz_*_ray :383-604, xz_*_ray :614-835).
-// lo/hi: planes izl/izu of S and alpha; prev: the previous (upwind) plane of I; zc = z[idz], zb1 = z[izl], zb2 = z[izu].
-// Centre values come from plane idz in the yz branch and from the UPPER plane izu in the xz branch.
-__global__ void k_reg_coef(RegPlane P, int up, double zc, double zb1, double zb2, const double* __restrict__ cj,
-                           const double* __restrict__ cs, const double* __restrict__ S_lo, const double* __restrict__ S_hi,
+// lo/hi: planes izl/izu of S and alpha; prev: the previous (upwind) plane of I; zc = z[idz], zb1 = z[izl], zb2 = z[izu];
+// r = |Δs / k_s| from the host.  Centre values come from plane idz in the yz branch and from the UPPER plane izu in the
+// xz branch: the host passes the right plane as S_c / a_c.
+__global__ void k_reg_coef(RegPlane P, int up, double r, double zc, double zb1, double zb2, const double* __restrict__ cj,
+                           const double* __restrict__ S_lo, const double* __restrict__ S_hi,
                            const double* __restrict__ a_lo, const double* __restrict__ a_hi, const double* __restrict__ S_c,
                            const double* __restrict__ a_c, const double* __restrict__ prev, double* __restrict__ cA,
                            double* __restrict__ cB, double* __restrict__ cC) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    const int l = blockIdx.y;
     if (idx >= P.np * P.ns) return;
     const int s = idx / P.np, j = idx - s * P.np;
     if (j < 1 || j > P.np - 2 || s < 1 || s > P.ns - 2) return;
-    const double r = fabs((cs[1] - cs[0]) / P.ks);
     const double zup = zc + r * P.kz;
     const double jup = cj[j] + r * P.kj;
     const int jl = j - (P.sgn_j + 1) / 2, ju = jl + 1;
     const int sn = s + P.sgn_s;
-    const double jb1 = cj[jl], jb2 = cj[ju];
-    const size_t base = (size_t)l * P.np * P.ns;
-    const size_t ol = base + (size_t)sn * P.np + jl, ou = ol + 1, oc = base + (size_t)s * P.np + j;
-    const double a_u = reg_bilinear(zup, jup, zb1, zb2, jb1, jb2, a_lo[ol], a_lo[ou], a_hi[ol], a_hi[ou]);
-    const double S_u = reg_bilinear(zup, jup, zb1, zb2, jb1, jb2, S_lo[ol], S_lo[ou], S_hi[ol], S_hi[ou]);
-    const double dtau = r * (a_c[oc] + a_u) / 2;
-    double a, b, e;
-    reg_weights(dtau, a, b, e);
-    const double p_l = prev[ol], p_u = prev[ou];
-    double I_fix, w_l, w_u;   // I_u = I_fix + w_l*car[jl] + w_u*car[ju]
-    if (up) {   // I_vals = [I_0 row; carried row]
-        I_fix = reg_bilinear(zup, jup, zb1, zb2, jb1, jb2, p_l, p_u, 0.0, 0.0);
-        w_l = reg_bilinear(zup, jup, zb1, zb2, jb1, jb2, 0.0, 0.0, 1.0, 0.0);
-        w_u = reg_bilinear(zup, jup, zb1, zb2, jb1, jb2, 0.0, 0.0, 0.0, 1.0);
-    } else {    // I_vals = [carried row; I_0 row]
-        I_fix = reg_bilinear(zup, jup, zb1, zb2, jb1, jb2, 0.0, 0.0, p_l, p_u);
-        w_l = reg_bilinear(zup, jup, zb1, zb2, jb1, jb2, 1.0, 0.0, 0.0, 0.0);
-        w_u = reg_bilinear(zup, jup, zb1, zb2, jb1, jb2, 0.0, 1.0, 0.0, 0.0);
+    const RegBil W(zup, jup, zb1, zb2, cj[jl], cj[ju]);
+    // I_u = I_fix + w_l*car[jl] + w_u*car[ju]: I_vals = [I_0 row; carried row] for up, [carried row; I_0 row] for down
+    const double w_l = up ? W(0.0, 0.0, 1.0, 0.0) : W(1.0, 0.0, 0.0, 0.0);
+    const double w_u = up ? W(0.0, 0.0, 0.0, 1.0) : W(0.0, 1.0, 0.0, 0.0);
+    const size_t pl = (size_t)P.np * P.ns;
+    const size_t ol = (size_t)sn * P.np + jl, ou = ol + 1, oc = (size_t)s * P.np + j;
+    const int l0 = blockIdx.y * REG_LPT, l1 = min(l0 + REG_LPT, P.lc);
+#pragma unroll
+    for (int q = 0; q < REG_LPT; q++) {
+        const int l = l0 + q;
+        if (l < l1) {
+            const size_t b = (size_t)l * pl;
+            const double a_u = W(a_lo[b + ol], a_lo[b + ou], a_hi[b + ol], a_hi[b + ou]);
+            const double S_u = W(S_lo[b + ol], S_lo[b + ou], S_hi[b + ol], S_hi[b + ou]);
+            const double dtau = r * (a_c[b + oc] + a_u) / 2;
+            double wa, wb, we;
+            reg_weights(dtau, wa, wb, we);
+            const double p_l = prev[b + ol], p_u = prev[b + ou];
+            const double I_fix = up ? W(p_l, p_u, 0.0, 0.0) : W(0.0, 0.0, p_l, p_u);
+            cA[b + oc] = we * w_l;
+            cB[b + oc] = we * w_u;
+            cC[b + oc] = we * I_fix + wa * S_u + wb * S_c[b + oc];
+        }
     }
-    cA[oc] = e * w_l;
-    cB[oc] = e * w_u;
-    cC[oc] = e * I_fix + a * S_u + b * S_c[oc];
 }
 
 __device__ __forceinline__ double reg_ldg(const double* p) {
@@ -485,17 +496,16 @@ int reg_plane_loop(const RegGeom& G, RegWorkspace& W, RegDir D, int n_sweeps, in
         if (branch) branch[idz] = cut;
         double* Ic = dI + pst * idz;
         const double* Iu = dI + pst * idu;
+        const dim3 grid((unsigned)((P.np * P.ns + 255) / 256), (unsigned)((n_l + REG_LPT - 1) / REG_LPT));
         if (cut == 1) {
-            const dim3 grid((unsigned)((P.np * P.ns + 255) / 256), (unsigned)n_l);
-            k_reg_xy<<<grid, 256>>>(P, hz[idu] - hz[idz], dcj, dcs, dS + pst * idz, dA + pst * idz, dS + pst * idu, dA + pst * idu, Iu, Ic);
+            k_reg_xy<<<grid, 256>>>(P, r_z, dcj, dcs, dS + pst * idz, dA + pst * idz, dS + pst * idu, dA + pst * idu, Iu, Ic);
             st->kernels += 1;
         } else {
             const int up = D.down ? 0 : 1;
             const int64_t izl = up ? idz - 1 : idz, izu = izl + 1;
             const int64_t izc = P.par_is_x ? izu : idz;          // Q13: xz takes the centre from the upper plane
-            const dim3 grid((unsigned)((P.np * P.ns + 255) / 256), (unsigned)n_l);
-            k_reg_coef<<<grid, 256>>>(P, up, hz[idz], hz[izl], hz[izu], dcj, dcs, dS + pst * izl, dS + pst * izu, dA + pst * izl,
-                                      dA + pst * izu, dS + pst * izc, dA + pst * izc, Iu, W.cA.p, W.cB.p, W.cC.p);
+            k_reg_coef<<<grid, 256>>>(P, up, P.par_is_x ? D.r_y : D.r_x, hz[idz], hz[izl], hz[izu], dcj, dS + pst * izl, dS + pst * izu,
+                                      dA + pst * izl, dA + pst * izu, dS + pst * izc, dA + pst * izc, Iu, W.cA.p, W.cB.p, W.cC.p);
             const int threads = ((P.np - 2 + 31) / 32) * 32;
             const size_t rec_smem = sizeof(double) * 2 * P.np;
             if (threads <= 512) k_reg_rec<512, REG_PF><<<(unsigned)n_l, threads, rec_smem>>>(P, n_sweeps, W.cA.p, W.cB.p, W.cC.p, Ic);
@@ -662,8 +672,17 @@ int regular_plan_chunk(const vrt_grid* g, int64_t nlam, double extra_vols, int64
     std::lock_guard<std::mutex> lock(g_reg_mu);
     RegWorkspace* Wp = nullptr;
     VRT_TRY(reg_workspace(&Wp));
-    // internal: S in both layouts, alpha in both, I
-    return reg_plan_chunk("regular solver", G, *Wp, nlam, 5.0 + extra_vols, 4.0, lc);
+    // internal: S, alpha and I of the direction being solved (regular_dir_accumulate holds one layout at a time)
+    return reg_plan_chunk("regular solver", G, *Wp, nlam, 3.0 + extra_vols, 4.0, lc);
+}
+
+int regular_dir_layout(const vrt_grid* g, const double k[3], int* layout) {
+    RegGeom G;
+    VRT_TRY(reg_geom_of(g, &G));
+    RegDir D;
+    VRT_TRY(reg_dir_setup("regular solver", G, k, 0, &D));
+    *layout = D.P.par_is_x;
+    return VRT_OK;
 }
 
 int regular_dir_accumulate(const vrt_grid* g, const double k[3], int down, int n_sweeps, int64_t n_l, const double* S, int64_t S_ld,
@@ -679,28 +698,30 @@ int regular_dir_accumulate(const vrt_grid* g, const double k[3], int down, int n
     RegWorkspace* Wp = nullptr;
     VRT_TRY(reg_workspace(&Wp));
     RegWorkspace& W = *Wp;
+    // one buffer each for S and alpha (slot 0), whatever the layout: the caller groups its directions by layout, so S is
+    // laid out twice per wavelength chunk, and the second slot's 2 volumes buy wider chunks instead
     const size_t need_vol = G.vol * n_l;
-    if (W.dI.n < need_vol || (W.dS[lay].p && W.dS[lay].n < need_vol) || (W.dA[lay].p && W.dA[lay].n < need_vol)) {
+    if (W.dI.n < need_vol || W.dS[0].n < need_vol || W.dA[0].n < need_vol || W.dS[1].p || W.dA[1].p) {
         W.release_arrays();
         have_S[0] = have_S[1] = false;
     }
-    if (!W.dS[lay].p) have_S[lay] = false;
     VRT_TRY(W.dI.ensure(need_vol));
-    VRT_TRY(W.dS[lay].ensure(need_vol));
-    VRT_TRY(W.dA[lay].ensure(need_vol));
+    VRT_TRY(W.dS[0].ensure(need_vol));
+    VRT_TRY(W.dA[0].ensure(need_vol));
     VRT_TRY(reg_common_buffers(G, W, n_l));
     if (!have_S[lay]) {
-        VRT_TRY(reg_load(G, S, true, G.nz, S_ld, S_l0, n_l, lay, W.dS[lay].p, W.stage, st));
+        VRT_TRY(reg_load(G, S, true, G.nz, S_ld, S_l0, n_l, lay, W.dS[0].p, W.stage, st));
         have_S[lay] = true;
+        have_S[1 - lay] = false;
     }
-    VRT_TRY(reg_load(G, alpha, true, G.nz, a_ld, a_l0, n_l, lay, W.dA[lay].p, W.stage, st));
+    VRT_TRY(reg_load(G, alpha, true, G.nz, a_ld, a_l0, n_l, lay, W.dA[0].p, W.stage, st));
     double* pl = W.dI.p + G.plane * n_l * (down ? G.nz - 1 : 0);
     if (I0) VRT_TRY(reg_load(G, I0, true, 1, n_l, 0, n_l, lay, pl, W.stage0, st));
     else VRT_CUDA(cudaMemsetAsync(pl, 0, sizeof(double) * G.plane * n_l));
     EvPair ev;
     VRT_TRY(ev.create());
     VRT_CUDA(cudaEventRecord(ev.a));
-    VRT_TRY(reg_plane_loop(G, W, D, n_sweeps, n_l, W.dS[lay].p, W.dA[lay].p, W.dI.p, st, nullptr));
+    VRT_TRY(reg_plane_loop(G, W, D, n_sweeps, n_l, W.dS[0].p, W.dA[0].p, W.dI.p, st, nullptr));
     VRT_CUDA(cudaEventRecord(ev.b));
     VRT_TRY(reg_store(G, W.dI.p, J, true, J_ld, J_l0, n_l, lay, w, accumulate, W.stage, st));
     VRT_CUDA(cudaDeviceSynchronize());

@@ -187,6 +187,8 @@ extern thread_local SweepStats g_last_stats;
 int regular_dir_accumulate(const vrt_grid* g, const double k[3], int down, int n_sweeps, int64_t n_l, const double* S, int64_t S_ld,
                            int64_t S_l0, const double* alpha, int64_t a_ld, int64_t a_l0, const double* I0, double* J, int64_t J_ld,
                            int64_t J_l0, double w, int accumulate, bool have_S[2], SweepStats* st);
+// internal layout (0: j = y, 1: j = x) a direction is solved in; callers group their directions by it
+int regular_dir_layout(const vrt_grid* g, const double k[3], int* layout);
 // wavelengths per chunk that fit next to `extra_vols` more volumes per wavelength held by the caller
 int regular_plan_chunk(const vrt_grid* g, int64_t nlam, double extra_vols, int64_t* lc);
 // S_new = (1-ε)J + εB with the criterion fused / the criterion alone, one wavelength (solver.cu; used by regular.cu)
