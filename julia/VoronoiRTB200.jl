@@ -192,6 +192,18 @@ function Λ_regular(ϵ::AbstractFloat, maxiter::Integer, atmos, quadrature::Stri
     return J * u"kW*m^-2*nm^-1", S * u"kW*m^-2*nm^-1", α_cont
 end
 
+# Λ_regular, NLTE line (src/lambda_iteration.jl:116-205): a regular-grid handle feeds the same engine as Λ_voronoi.  Every
+# per-site array is the (nz, nx, ny) Julia array as it lies in memory; S, J are (nλ, nz, nx, ny), populations (nz, nx, ny, 3).
+function regular_grid(atmos)
+    z = Float64.(ustrip.(u"m", atmos.z)); x = Float64.(ustrip.(u"m", atmos.x)); y = Float64.(ustrip.(u"m", atmos.y))
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:vrt_regular_grid_create, libvrt), Cint, (Int64, Int64, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ref{Ptr{Cvoid}}),
+                length(z), length(x), length(y), z, x, y, h))
+    return Grid(h[], length(z) * length(x) * length(y))
+end
+# Λ_regular(ϵ, maxiter, atmos, line, quadrature, DATA; …) is Λ_voronoi above with `grid_of(sites)` replaced by
+# `regular_grid(atmos)`, `sites.*` by `atmos.*` and the results reshaped to (nλ, nz, nx, ny) / (nz, nx, ny, 3).
+
 function readdlm_quadrature(fname)
     rows = [parse.(Float64, split(l)) for l in eachline(fname) if !isempty(strip(l))]
     return permutedims(hcat(rows...))
