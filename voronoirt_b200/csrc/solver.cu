@@ -635,9 +635,11 @@ static int plan_buffers(vrt_solver* s) {
     auto fits = [&](int64_t lcc, int dbb) { return rows_max * dbb * (double)lcc * 8.0 <= budget; };
     // The sweep costs per (cell, direction) visit and per pass, far more than per byte: wide wavelength rows come first
     // (fewer passes over the visit lists, wide TMA rows), then as many directions in flight as still fit.  At least
-    // min(nd, 4) directions are kept in flight because the dataflow order hides dependency latency behind the other
-    // directions' work (measured: 2 directions in flight cost 30 % more than 6 or more).
-    const int db_min = std::min(db, 4);
+    // min(nd, 2) directions are kept in flight because the dataflow order hides dependency latency behind the other
+    // directions' work.  Measured: on 1 M sites 2 directions in flight cost 33 % more than 6 or more, but a second pass
+    // over half-width rows costs 71 % more; on 16 M sites (91 wavelengths x 2 directions) beats (46 x 4) by 24 %
+    // (profiles/README.md), so the width wins down to two directions.
+    const int db_min = std::min(db, 2);
     if (s->cfg.lam_chunk <= 0 && !(envl && atoi(envl) > 0)) {
         if (!fits(lc, db_min)) lc = std::max<int64_t>(1, (int64_t)(budget / (rows_max * db_min * 8.0)));
         // even out the chunks: ceil(nlam / passes)
