@@ -141,6 +141,15 @@ int vrt_set_device(int32_t device);
  * then again with an n x ld int64 buffer (column-major, zero-filled by the library). */
 int vrt_read_neighbours(const char* fname, int64_t n, int64_t* nbr, int64_t ld, int64_t* ld_needed);
 
+/* Native Voronoi neighbour generation on the GPU: what the voro++ driver
+ * (rt_preprocessing/output_sites.cc:35-49: container periodic in x and y, walls in z, `print_custom("%i %n")`), its text
+ * files (io.jl:8-40) and vrt_read_neighbours produce together.  positions: 3 x n rows (z, x, y); bounds: z_min, z_max,
+ * x_min, x_max, y_min, y_max.  nbr: n x ld column-major, column 0 = number of faces, then the 1-based ids of the face
+ * neighbours, -5 / -6 for the z_min / z_max walls; the SETS equal voro++'s, the order inside a row is not voro++'s (the
+ * reference does not define it).  ld_needed (optional) receives max faces + 1; call with nbr == NULL to get it first, or
+ * pass ld = 64 (the per-cell capacity) and trim.  VRT_E_GRID when a cell exceeds the capacity. */
+int vrt_voronoi_neighbours(int64_t n, const double* positions, const double bounds[6], int64_t* nbr, int64_t ld, int64_t* ld_needed);
+
 /* Build the grid: layers from the bottom/top wall (_sort_by_layer_up/_down, voronoi_utils.jl:93-174),
  * stable sort permutations and reduce_layers offsets (:71-79,:253-269), unit Delaunay edge vectors
  * (calc_Delaunay_lines, :186-245).  bounds = {z_min,z_max,x_min,x_max,y_min,y_max}. */

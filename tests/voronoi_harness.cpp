@@ -1,0 +1,45 @@
+// CPU harness for voronoirt_b200/csrc/voronoi_cell.cuh — TEST INFRASTRUCTURE ONLY (built and loaded by
+// tests/test_voronoi_native.py).  It compiles the same host/device cell code the CUDA kernel uses, so the geometry can
+// be checked against voro++'s neighbour lists (tests/golden/*.npz) without a GPU.  Not part of the product.
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+#include "../voronoirt_b200/csrc/voronoi_cell.cuh"
+
+using namespace vrt;
+
+extern "C" int vc_harness(int64_t n, const double* pos, const double* bounds, int gx, int gy, int gz, int64_t* nbr, int64_t ld,
+                          int32_t* status) {
+    VoroGrid G;
+    G.gx = gx; G.gy = gy; G.gz = gz;
+    G.z0 = bounds[0]; G.Lz = bounds[1] - bounds[0];
+    G.x0 = bounds[2]; G.Lx = bounds[3] - bounds[2];
+    G.y0 = bounds[4]; G.Ly = bounds[5] - bounds[4];
+    G.hx = G.Lx / gx; G.hy = G.Ly / gy; G.hz = G.Lz / gz;
+    const int64_t nc = (int64_t)gx * gy * gz;
+    std::vector<int32_t> start(nc + 1, 0), order(n), cellof(n);
+    for (int64_t i = 0; i < n; i++) {
+        int ix = (int)((pos[3 * i + 1] - G.x0) / G.hx), iy = (int)((pos[3 * i + 2] - G.y0) / G.hy), iz = (int)((pos[3 * i] - G.z0) / G.hz);
+        ix = ix < 0 ? 0 : (ix >= gx ? gx - 1 : ix);
+        iy = iy < 0 ? 0 : (iy >= gy ? gy - 1 : iy);
+        iz = iz < 0 ? 0 : (iz >= gz ? gz - 1 : iz);
+        cellof[i] = (int32_t)(ix + gx * (iy + gy * iz));
+        start[cellof[i] + 1]++;
+    }
+    for (int64_t c = 0; c < nc; c++) start[c + 1] += start[c];
+    std::vector<int32_t> fill(start.begin(), start.end() - 1);
+    for (int64_t i = 0; i < n; i++) order[fill[cellof[i]]++] = (int32_t)i;
+    G.start = start.data(); G.order = order.data(); G.pos = pos;
+    int bad = 0;
+    ConvexCell* cell = new ConvexCell();
+    for (int64_t i = 0; i < n; i++) {
+        int64_t* row = nbr + i * ld;
+        int cnt = voronoi_cell_of(G, n, i, *cell, row + 1, (int)(ld - 1));
+        status[i] = cell->status;
+        row[0] = cnt;
+        if (cnt < 0 || cnt > ld - 1) bad++;
+    }
+    delete cell;
+    return bad;
+}

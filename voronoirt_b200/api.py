@@ -75,6 +75,19 @@ def voro(voro_executable, sites_file, neighbours_file, x_min, x_max, y_min, y_ma
 
 
 # ------------------------------------------------------------------ voronoi_utils.jl
+def voronoi_neighbours(positions, z_min, z_max, x_min, x_max, y_min, y_max):
+    """Native replacement of write_arrays + voro + the parsing half of read_cell (src/io.jl:8-40,
+    rt_preprocessing/output_sites.cc, src/voronoi_utils.jl:42-70): positions (3, n) rows (z, x, y) -> NeighbourMatrix
+    (n, ld) int64 with the same neighbour sets as voro++ (row order differs, see include/vrt.h)."""
+    pos = _f(positions)
+    n = pos.shape[1]
+    b = np.array([z_min, z_max, x_min, x_max, y_min, y_max], dtype=np.float64)
+    nbr = np.zeros((n, 64), dtype=np.int64, order="F")
+    need = C.c_int64()
+    check(lib().vrt_voronoi_neighbours(n, _ptr(pos), _ptr(b), _ptr(nbr), 64, C.byref(need)))
+    return np.asfortranarray(nbr[:, :need.value])
+
+
 class _Grid:
     """owner of a vrt_grid handle"""
 

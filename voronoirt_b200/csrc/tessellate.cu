@@ -1,0 +1,183 @@
+// tessellate.cu — native Voronoi neighbour generation on the GPU.
+//
+// Replaces the reference's preprocessing round trip: write_arrays (io.jl:8-40) -> the single-threaded voro++ driver
+// (rt_preprocessing/output_sites.cc: container periodic in x, y, walls in z, `print_custom("%i %n")`) -> the text parser of
+// read_cell (voronoi_utils.jl:42-70).  Output is the NeighbourMatrix read_cell builds: n x ld, column 0 = number of
+// faces, then the 1-based ids of the face neighbours, -5 / -6 for the z_min / z_max walls.  The neighbour SETS equal
+// voro++'s (tests: the committed voro++ lists of tests/golden/*.npz, and a 100 k-site stratified box); the order inside a
+// row is this file's (box planes first, then by ring of the search grid), not voro++'s, which the reference leaves undefined.
+//
+// K-T1 k_vt_cell_index: uniform grid cell of every site;  CUB radix sort by cell;  K-T2 k_vt_cell_start: offsets;
+// K-T3 k_vt_cells: one thread per site (in cell order, so neighbouring threads walk the same grid cells) clips its cell
+// with voronoi_cell.cuh; the cell (planes + dual triangles, 6 KB) lives in thread-local memory;  K-T4 k_vt_emit: rows of the
+// int32 scratch -> the caller's column-major int64 matrix.
+#include <algorithm>
+#include <math.h>
+#include <cub/cub.cuh>
+#include "voronoi_cell.cuh"
+#include "vrt_internal.h"
+
+namespace vrt {
+namespace {
+
+constexpr int VT_CAP = 64;   // faces per cell the scratch can hold (column 0 + 63 ids)
+
+__global__ void k_vt_cell_index(int64_t n, const double* __restrict__ pos, VoroGrid G, int32_t* __restrict__ cell, int32_t* __restrict__ iota) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int ix = (int)((pos[3 * i + 1] - G.x0) / G.hx), iy = (int)((pos[3 * i + 2] - G.y0) / G.hy), iz = (int)((pos[3 * i] - G.z0) / G.hz);
+    ix = ix < 0 ? 0 : (ix >= G.gx ? G.gx - 1 : ix);
+    iy = iy < 0 ? 0 : (iy >= G.gy ? G.gy - 1 : iy);
+    iz = iz < 0 ? 0 : (iz >= G.gz ? G.gz - 1 : iz);
+    cell[i] = ix + G.gx * (iy + G.gy * iz);
+    iota[i] = (int32_t)i;
+}
+
+// start[c] = first position in the sorted list whose cell is >= c (start has nc + 1 entries)
+__global__ void k_vt_cell_start(int64_t n, int64_t nc, const int32_t* __restrict__ sorted_cell, int32_t* __restrict__ start) {
+    const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (k > n) return;
+    const int64_t lo = k == 0 ? 0 : (int64_t)sorted_cell[k - 1] + 1;
+    const int64_t hi = k == n ? nc : (int64_t)sorted_cell[k];
+    for (int64_t c = lo; c <= hi; c++) start[c] = (int32_t)k;
+}
+
+__global__ void __launch_bounds__(128) k_vt_cells(int64_t n, VoroGrid G, int32_t* __restrict__ rows, int32_t* __restrict__ status) {
+    const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const int64_t i = G.order[k];
+    ConvexCell cell;
+    int64_t ids[VT_CAP];
+    const int cnt = voronoi_cell_of(G, n, i, cell, ids, VT_CAP - 1);
+    int32_t* row = rows + i * VT_CAP;
+    int st = cell.status;
+    if (st == VC_OK && cnt > VT_CAP - 1) st = VC_OVERFLOW;
+    status[i] = st;
+    row[0] = st == VC_OK ? cnt : 0;
+    if (st == VC_OK)
+        for (int q = 0; q < cnt; q++) row[1 + q] = (int32_t)ids[q];
+}
+
+__global__ void k_vt_emit(int64_t n, int64_t ld, const int32_t* __restrict__ rows, int64_t* __restrict__ nbr) {
+    const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (idx >= n * ld) return;
+    const int64_t c = idx / n, i = idx - c * n;   // column-major: consecutive threads write consecutive rows of a column
+    const int32_t cnt = rows[i * VT_CAP];
+    nbr[idx] = c == 0 ? cnt : (c <= cnt && c < VT_CAP ? rows[i * VT_CAP + c] : 0);
+}
+
+struct MaxStatus {
+    int32_t max_cnt, bad;
+};
+
+__global__ void k_vt_reduce(int64_t n, const int32_t* __restrict__ rows, const int32_t* __restrict__ status, int32_t* __restrict__ out) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    atomicMax(&out[0], rows[i * VT_CAP]);
+    if (status[i] != VC_OK) atomicAdd(&out[1], 1);
+}
+
+}  // namespace
+}  // namespace vrt
+
+using namespace vrt;
+
+extern "C" int vrt_voronoi_neighbours(int64_t n, const double* positions, const double bounds[6], int64_t* nbr, int64_t ld,
+                                      int64_t* ld_needed) {
+    if (n <= 0 || !positions || !bounds || n >= ((int64_t)1 << 31)) {
+        set_error("vrt_voronoi_neighbours: bad arguments");
+        return VRT_E_INVALID;
+    }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        set_error("vrt_voronoi_neighbours: no CUDA device (this library has no CPU path)");
+        return VRT_E_CUDA;
+    }
+    double hb[6];
+    VRT_CUDA(cudaMemcpy(hb, bounds, sizeof(hb), cudaMemcpyDefault));
+    VoroGrid G;
+    G.z0 = hb[0]; G.Lz = hb[1] - hb[0];
+    G.x0 = hb[2]; G.Lx = hb[3] - hb[2];
+    G.y0 = hb[4]; G.Ly = hb[5] - hb[4];
+    if (!(G.Lx > 0) || !(G.Ly > 0) || !(G.Lz > 0)) {
+        set_error("vrt_voronoi_neighbours: empty box");
+        return VRT_E_INVALID;
+    }
+    // near-cubic search cells with about four sites each
+    const double h = cbrt(G.Lx * G.Ly * G.Lz * 4.0 / (double)n);
+    auto cells = [&](double L) { return (int)std::max<int64_t>(1, std::min<int64_t>(1024, llround(L / h))); };
+    G.gx = cells(G.Lx); G.gy = cells(G.Ly); G.gz = cells(G.Lz);
+    G.hx = G.Lx / G.gx; G.hy = G.Ly / G.gy; G.hz = G.Lz / G.gz;
+    const int64_t nc = (int64_t)G.gx * G.gy * G.gz;
+
+    DevBuf<double> dpos;
+    const double* pos = positions;
+    if (!is_device_ptr(positions)) {
+        VRT_TRY(dpos.alloc((size_t)3 * n));
+        VRT_CUDA(cudaMemcpy(dpos.p, positions, sizeof(double) * 3 * (size_t)n, cudaMemcpyHostToDevice));
+        pos = dpos.p;
+    }
+    DevBuf<int32_t> cell, cell_sorted, iota, order, start, rows, status, red;
+    VRT_TRY(cell.alloc(n)); VRT_TRY(cell_sorted.alloc(n)); VRT_TRY(iota.alloc(n)); VRT_TRY(order.alloc(n));
+    VRT_TRY(start.alloc(nc + 1)); VRT_TRY(rows.alloc((size_t)n * VT_CAP)); VRT_TRY(status.alloc(n)); VRT_TRY(red.alloc(2));
+    cudaEvent_t e0, e1;
+    VRT_CUDA(cudaEventCreate(&e0));
+    VRT_CUDA(cudaEventCreate(&e1));
+    struct EvGuard { cudaEvent_t a, b; ~EvGuard() { cudaEventDestroy(a); cudaEventDestroy(b); } } evg{e0, e1};
+    VRT_CUDA(cudaEventRecord(e0));
+    const int bs = 256;
+    k_vt_cell_index<<<(unsigned)((n + bs - 1) / bs), bs>>>(n, pos, G, cell.p, iota.p);
+    VRT_CUDA(cudaGetLastError());
+    {
+        size_t tmp_bytes = 0;
+        int bits = 1;
+        while (((int64_t)1 << bits) < nc) bits++;
+        VRT_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, cell.p, cell_sorted.p, iota.p, order.p, (int)n, 0, bits));
+        DevBuf<char> tmp;
+        VRT_TRY(tmp.alloc(tmp_bytes));
+        VRT_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, cell.p, cell_sorted.p, iota.p, order.p, (int)n, 0, bits));
+    }
+    k_vt_cell_start<<<(unsigned)((n + 1 + bs - 1) / bs), bs>>>(n, nc, cell_sorted.p, start.p);
+    VRT_CUDA(cudaGetLastError());
+    G.start = start.p; G.order = order.p; G.pos = pos;
+    k_vt_cells<<<(unsigned)((n + 127) / 128), 128>>>(n, G, rows.p, status.p);
+    VRT_CUDA(cudaGetLastError());
+    VRT_CUDA(cudaMemset(red.p, 0, sizeof(int32_t) * 2));
+    k_vt_reduce<<<(unsigned)((n + bs - 1) / bs), bs>>>(n, rows.p, status.p, red.p);
+    VRT_CUDA(cudaGetLastError());
+    VRT_CUDA(cudaEventRecord(e1));
+    int32_t hred[2] = {0, 0};
+    VRT_CUDA(cudaMemcpy(hred, red.p, sizeof(hred), cudaMemcpyDeviceToHost));
+    float ms = 0;
+    VRT_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    SweepStats st;
+    st.kernels = 6;   // index, 2 sort passes counted as one each, start, cells, reduce (+ emit below)
+    st.sweep_ms = ms;
+    if (hred[1] > 0) {
+        set_error("vrt_voronoi_neighbours: %d cells exceed the per-cell capacity (%d planes / %d faces): degenerate input?", (int)hred[1],
+                  VC_MAXP, VT_CAP - 1);
+        return VRT_E_GRID;
+    }
+    if (ld_needed) *ld_needed = (int64_t)hred[0] + 1;
+    if (nbr) {
+        if (ld < (int64_t)hred[0] + 1) {
+            set_error("vrt_voronoi_neighbours: ld = %lld but %d columns are needed", (long long)ld, (int)hred[0] + 1);
+            return VRT_E_INVALID;
+        }
+        DevBuf<int64_t> dout;
+        int64_t* out = nbr;
+        const bool dev_out = is_device_ptr(nbr);
+        if (!dev_out) {
+            VRT_TRY(dout.alloc((size_t)n * ld));
+            out = dout.p;
+        }
+        k_vt_emit<<<(unsigned)(((size_t)n * ld + bs - 1) / bs), bs>>>(n, ld, rows.p, out);
+        VRT_CUDA(cudaGetLastError());
+        st.kernels += 1;
+        if (!dev_out) VRT_CUDA(cudaMemcpy(nbr, dout.p, sizeof(int64_t) * (size_t)n * ld, cudaMemcpyDeviceToHost));
+    }
+    VRT_CUDA(cudaDeviceSynchronize());
+    g_last_stats = st;
+    return VRT_OK;
+}
