@@ -37,6 +37,9 @@ WORKLOADS = {
     "nlte_1m_direct": (1000000, 1, 1, "ul7n12", 50, 20),   # 1 M sites tessellated directly (no tiling): slower set-up, same solve
     "nlte_4m": (250000, 4, 4, "ul9n20", 50, 20),
     "nlte_16m": (250000, 8, 8, "ul9n20", 50, 20),
+    # directly sampled sites, tessellated on the GPU by vrt_voronoi_neighbours (no voro++, no tiling)
+    "nlte_4m_native": (4000000, 1, 1, "ul9n20", 50, 20),
+    "nlte_16m_native": (16000000, 1, 1, "ul9n20", 50, 20),
     # BASELINE configs[3]: the regular-grid comparison solver, 256 x 256 x 400 (+ ghost columns), ul7n12, 91 wavelengths (N = 1 only)
     "regular_400": (0, 1, 1, "ul7n12", 50, 20),
 }
@@ -55,6 +58,16 @@ def build_problem(workload):
     os.makedirs(cache, exist_ok=True)
     f = os.path.join(cache, f"base_{base}_seed2022.npz")
     rank = int(os.environ.get("RANK", "0"))
+    if workload.endswith("_native"):
+        t = time.time()
+        pos = synth.sample_sites(base, seed=2022)
+        t1 = time.time()
+        B = synth.BOX
+        nbr = api.voronoi_neighbours(pos, B["z_min"], B["z_max"], B["x_min"], B["x_max"], B["y_min"], B["y_max"])
+        log(f"sampled {base} sites in {t1 - t:.1f}s, tessellated them on the GPU in {time.time() - t1:.2f}s (max {int(nbr[:, 0].max())} faces)")
+        atm = synth.atmosphere(pos[0], pos[1], pos[2])
+        return dict(pos=pos, nbr=nbr, bounds=dict(synth.BOX), atm=atm, n=pos.shape[1], qpath=api.quadrature_path(qname), qname=qname,
+                    nbb=nbb, nbf=nbf, tiles=(1, 1), base=base, native=True)
     if not os.path.exists(f):
         if rank == 0:
             t = time.time()
@@ -592,6 +605,8 @@ def main_regular(args, W, K):
 def workload_name(key, P, nlam):
     kx, ky = P["tiles"]
     tile = f" (voro++ tessellation of {P['base']} sites tiled {kx}x{ky} periodically)" if kx * ky > 1 else ""
+    if P.get("native"):
+        tile = " (sampled directly, tessellated on the GPU by vrt_voronoi_neighbours)"
     return f"{key}: NLTE line Lambda-iteration, {P['n']} Voronoi sites{tile}, {P['qname']}, {nlam} wavelengths, synthetic Bifrost-shaped atmosphere"
 
 
