@@ -150,6 +150,14 @@ int vrt_read_neighbours(const char* fname, int64_t n, int64_t* nbr, int64_t ld, 
  * pass ld = 64 (the per-cell capacity) and trim.  VRT_E_GRID when a cell exceeds the capacity. */
 int vrt_voronoi_neighbours(int64_t n, const double* positions, const double bounds[6], int64_t* nbr, int64_t ld, int64_t* ld_needed);
 
+/* trilinear (functions.jl:207-248), broadcast over the sites: vals is a (nz, nx, ny) field on the atmosphere axes z, x, y,
+ * positions 3 x n rows (z, x, y), out n.  initialise (voronoi_utils.jl:687-708) is six such calls (temperature, electron
+ * density, hydrogen density, velocity z, x, y).  Corner search as searchsortedfirst - 1; the lerps in the reference's order
+ * with every operation rounded separately (bit-exact against an IEEE evaluation of the Julia expressions).  Sites
+ * outside the axes, where the reference throws a BoundsError, get NaN and the call returns VRT_E_INVALID. */
+int vrt_trilinear(int64_t nz, int64_t nx, int64_t ny, const double* z, const double* x, const double* y,
+                  const double* vals, int64_t n, const double* positions, double* out);
+
 /* Build the grid: layers from the bottom/top wall (_sort_by_layer_up/_down, voronoi_utils.jl:93-174),
  * stable sort permutations and reduce_layers offsets (:71-79,:253-269), unit Delaunay edge vectors
  * (calc_Delaunay_lines, :186-245).  bounds = {z_min,z_max,x_min,x_max,y_min,y_max}. */

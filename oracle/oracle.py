@@ -298,3 +298,16 @@ def lambda_regular_line(z, x, y, line, lam, sd, quad, S0, pops0, eps=1e-3, maxit
                                        _p(lam), C.byref(sd), C.byref(quad), C.c_int(n_sweeps), C.c_double(eps), C.c_int(maxiter),
                                        _p(S), _p(J), _p(pops), _p(conv))
     return J, S, pops, conv, it
+
+
+def trilinear(z, x, y, vals, positions):
+    """functions.jl:207-248 over the columns of positions (3, n) rows (z, x, y); vals (nz, nx, ny) -> (out (n,), n_outside)"""
+    z, x, y = map(f64, (z, x, y))
+    vals = np.asfortranarray(vals, dtype=np.float64)
+    pos = np.asfortranarray(positions, dtype=np.float64)
+    n = pos.shape[1]
+    out = np.zeros(n)
+    L = lib()
+    L.orc_trilinear.restype = C.c_int64
+    bad = L.orc_trilinear(C.c_int64(len(z)), C.c_int64(len(x)), C.c_int64(len(y)), _p(z), _p(x), _p(y), _p(vals), C.c_int64(n), _p(pos), _p(out))
+    return out, int(bad)

@@ -289,3 +289,36 @@ int orc_lambda_regular(int64_t nz, int64_t nx, int64_t ny, const double* z, cons
     free(I0);
     return i;
 }
+
+/* trilinear (functions.jl:207-248) broadcast over n sites; vals (nz, nx, ny) column-major, pos 3 x n rows (z, x, y).
+ * searchsortedfirst(a, x) - 1 = (number of elements < x) - 1 as a 0-based lower corner.  Out-of-range sites (BoundsError
+ * in Julia) give NaN; returns their number.  Compiled with -ffp-contract=off: every operation rounds on its own. */
+static int64_t orc_lower_corner(const double* a, int64_t n, double x) {
+    int64_t c = 0;
+    while (c < n && a[c] < x) c++;
+    return c - 1;
+}
+int64_t orc_trilinear(int64_t nz, int64_t nx, int64_t ny, const double* z, const double* x, const double* y, const double* vals,
+                      int64_t n, const double* pos, double* out) {
+    int64_t bad = 0;
+    for (int64_t k = 0; k < n; k++) {
+        double zm = pos[3 * k], xm = pos[3 * k + 1], ym = pos[3 * k + 2];
+        int64_t iz = orc_lower_corner(z, nz, zm), ix = orc_lower_corner(x, nx, xm), iy = orc_lower_corner(y, ny, ym);
+        if (iz < 0 || iz > nz - 2 || ix < 0 || ix > nx - 2 || iy < 0 || iy > ny - 2) { out[k] = NAN; bad++; continue; }
+        double x_d = (xm - x[ix]) / (x[ix + 1] - x[ix]);
+        double y_d = (ym - y[iy]) / (y[iy + 1] - y[iy]);
+        double z_d = (zm - z[iz]) / (z[iz + 1] - z[iz]);
+#define VV(a, b, c) vals[(a) + nz * ((b) + nx * (c))]
+        double c000 = VV(iz, ix, iy), c010 = VV(iz, ix, iy + 1), c100 = VV(iz, ix + 1, iy), c110 = VV(iz, ix + 1, iy + 1);
+        double c001 = VV(iz + 1, ix, iy), c011 = VV(iz + 1, ix, iy + 1), c101 = VV(iz + 1, ix + 1, iy), c111 = VV(iz + 1, ix + 1, iy + 1);
+#undef VV
+        double c00 = c000 * (1 - x_d) + c100 * x_d;
+        double c01 = c001 * (1 - x_d) + c101 * x_d;
+        double c10 = c010 * (1 - x_d) + c110 * x_d;
+        double c11 = c011 * (1 - x_d) + c111 * x_d;
+        double c0 = c00 * (1 - y_d) + c10 * y_d;
+        double c1 = c01 * (1 - y_d) + c11 * y_d;
+        out[k] = c0 * (1 - z_d) + c1 * z_d;
+    }
+    return bad;
+}

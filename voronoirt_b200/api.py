@@ -88,6 +88,24 @@ def voronoi_neighbours(positions, z_min, z_max, x_min, x_max, y_min, y_max):
     return np.asfortranarray(nbr[:, :need.value])
 
 
+def trilinear(positions, atmos, vals):
+    """src/functions.jl:207-248 broadcast over the sites: positions (3, n) rows (z, x, y), vals (nz, nx, ny) -> (n,)"""
+    pos = _f(positions)
+    v = _f(vals)
+    if v.shape != atmos.shape:
+        raise ValueError("vals must be (nz, nx, ny)")
+    out = np.zeros(pos.shape[1])
+    check(lib().vrt_trilinear(atmos.shape[0], atmos.shape[1], atmos.shape[2], _ptr(atmos.z), _ptr(atmos.x), _ptr(atmos.y), _ptr(v),
+                              pos.shape[1], _ptr(pos), _ptr(out)))
+    return out
+
+
+def initialise(p_vec, atmos):
+    """src/voronoi_utils.jl:687-708 -> (temperature, N_e, N_H, velocity_z, velocity_x, velocity_y) at the sites"""
+    return tuple(trilinear(p_vec, atmos, f) for f in (atmos.temperature, atmos.electron_density, atmos.hydrogen_populations,
+                                                      atmos.velocity_z, atmos.velocity_x, atmos.velocity_y))
+
+
 class _Grid:
     """owner of a vrt_grid handle"""
 
