@@ -158,6 +158,13 @@ int vrt_voronoi_neighbours(int64_t n, const double* positions, const double boun
 int vrt_trilinear(int64_t nz, int64_t nx, int64_t ny, const double* z, const double* x, const double* y,
                   const double* vals, int64_t n, const double* positions, double* out);
 
+/* Nearest site of each of m points (3 x m rows (z, x, y)): the `nn(KDTree(ustrip.(sites.positions)), p)` of the
+ * Voronoi -> raster resampling (voronoi_utils.jl:441-444 and its variants :479-771): plain Euclidean distance, no periodic
+ * wrap.  idx: 1-based site ids (ties go to the smaller id), dist (optional): the distances.  The gathers that follow in the
+ * reference (temperature[k,i,j] = sites.temperature[idx] ...) stay with the host. */
+int vrt_nearest_site(int64_t n, const double* positions, const double bounds[6], int64_t m, const double* points,
+                     int64_t* idx, double* dist);
+
 /* Build the grid: layers from the bottom/top wall (_sort_by_layer_up/_down, voronoi_utils.jl:93-174),
  * stable sort permutations and reduce_layers offsets (:71-79,:253-269), unit Delaunay edge vectors
  * (calc_Delaunay_lines, :186-245).  bounds = {z_min,z_max,x_min,x_max,y_min,y_max}. */

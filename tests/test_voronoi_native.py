@@ -38,7 +38,7 @@ def harness():
     d = tempfile.mkdtemp(prefix="vrt_vc_")
     so = os.path.join(d, "libvc_harness.so")
     gxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
-    subprocess.run([gxx, "-O2", "-std=c++17", "-shared", "-fPIC", "-o", so, os.path.join(HERE, "voronoi_harness.cpp")], check=True)
+    subprocess.run([gxx, "-O2", "-std=c++17", "-ffp-contract=off", "-shared", "-fPIC", "-o", so, os.path.join(HERE, "voronoi_harness.cpp")], check=True)
     return C.CDLL(so)
 
 
@@ -107,3 +107,53 @@ def test_gpu_neighbours_drive_the_solver_like_voro_lists():
     cell_b = V.read_cell(gold, n, pos, b[2], b[3], b[4], b[5])
     assert np.array_equal(cell_a[3], cell_b[3]) and np.array_equal(cell_a[4], cell_b[4])      # layers_up / layers_down
     assert np.array_equal(cell_a[5], cell_b[5]) and np.array_equal(cell_a[6], cell_b[6])      # perm_up / perm_down
+
+
+def brute_force_nn(pos, q):
+    """argmin over the sites of (dz^2 + dx^2) + dy^2, first minimum; pos (3, n), q (3, m)"""
+    d = (pos.T[None, :, :] - q.T[:, None, :]) ** 2
+    d2 = (d[:, :, 0] + d[:, :, 1]) + d[:, :, 2]
+    return d2.argmin(axis=1) + 1, np.sqrt(d2.min(axis=1))
+
+
+def queries(b, m, rng):
+    """points inside the box, on its faces and a little outside"""
+    q = np.stack([rng.uniform(b[0], b[1], m), rng.uniform(b[2], b[3], m), rng.uniform(b[4], b[5], m)])
+    q[0, :50] = b[0]; q[1, 50:100] = b[3]; q[2, 100:150] = b[5]
+    q[:, 150:200] += (np.array([b[1] - b[0], b[3] - b[2], b[5] - b[4]]) * 0.05)[:, None]
+    return np.asfortranarray(q)
+
+
+def test_nearest_site_core_equals_brute_force(harness):
+    pos, gold, b = load_grid("grid_strat3000")
+    q = queries(b, 4000, np.random.default_rng(3))
+    idx = np.zeros(q.shape[1], dtype=np.int64)
+    d2 = np.zeros(q.shape[1])
+    p = np.ascontiguousarray(pos.T)
+    qq = np.ascontiguousarray(q.T)
+    harness.vc_nn_harness(C.c_int64(pos.shape[1]), p.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p), 8, 8, 13, C.c_int64(q.shape[1]),
+                          qq.ctypes.data_as(C.c_void_p), idx.ctypes.data_as(C.c_void_p), d2.ctypes.data_as(C.c_void_p))
+    ref, dist = brute_force_nn(pos, q)
+    assert np.array_equal(idx, ref) and np.array_equal(np.sqrt(d2), dist)
+
+
+@pytest.mark.gpu
+def test_gpu_nearest_site_and_raster():
+    import voronoirt_b200 as V
+    pos, gold, b = load_grid("grid_strat3000")
+    q = queries(b, 4000, np.random.default_rng(4))
+    idx, dist = V.nearest_site(pos, b, q)
+    ref, rdist = brute_force_nn(pos, q)
+    assert np.array_equal(idx, ref) and np.array_equal(dist, rdist)
+    # Voronoi_to_Raster: rasters of per-site fields (voronoi_utils.jl:436-455)
+    n = pos.shape[1]
+    cell = V.read_cell(gold, n, pos, b[2], b[3], b[4], b[5])
+    rng = np.random.default_rng(5)
+    T, S = rng.uniform(4e3, 1e4, n), rng.uniform(0, 1, (7, n))
+    sites = V.VoronoiSites(*cell, T, T, T, T, T, T, b[0], b[1], b[2], b[3], b[4], b[5], n)
+    z, x, y = np.linspace(b[0], b[1], 9), np.linspace(b[2], b[3], 6), np.linspace(b[4], b[5], 5)
+    ridx, Tg, Sg = V.Voronoi_to_Raster(sites, z, x, y, T, S)
+    Z, X, Y = np.meshgrid(z, x, y, indexing="ij")
+    want, _ = brute_force_nn(pos, np.stack([Z.ravel(), X.ravel(), Y.ravel()]))
+    assert np.array_equal(ridx.ravel(), want)
+    assert np.array_equal(Tg, T[ridx - 1]) and np.array_equal(Sg, S[:, ridx - 1]) and Sg.shape == (7, 9, 6, 5)

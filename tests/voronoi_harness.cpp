@@ -9,6 +9,39 @@
 
 using namespace vrt;
 
+static void build_grid(int64_t n, const double* pos, const double* bounds, int gx, int gy, int gz, VoroGrid& G, std::vector<int32_t>& start,
+                       std::vector<int32_t>& order) {
+    G.gx = gx; G.gy = gy; G.gz = gz;
+    G.z0 = bounds[0]; G.Lz = bounds[1] - bounds[0];
+    G.x0 = bounds[2]; G.Lx = bounds[3] - bounds[2];
+    G.y0 = bounds[4]; G.Ly = bounds[5] - bounds[4];
+    G.hx = G.Lx / gx; G.hy = G.Ly / gy; G.hz = G.Lz / gz;
+    const int64_t nc = (int64_t)gx * gy * gz;
+    start.assign(nc + 1, 0);
+    order.resize(n);
+    std::vector<int32_t> cellof(n);
+    for (int64_t i = 0; i < n; i++) {
+        int ix = (int)((pos[3 * i + 1] - G.x0) / G.hx), iy = (int)((pos[3 * i + 2] - G.y0) / G.hy), iz = (int)((pos[3 * i] - G.z0) / G.hz);
+        ix = ix < 0 ? 0 : (ix >= gx ? gx - 1 : ix);
+        iy = iy < 0 ? 0 : (iy >= gy ? gy - 1 : iy);
+        iz = iz < 0 ? 0 : (iz >= gz ? gz - 1 : iz);
+        cellof[i] = (int32_t)(ix + gx * (iy + gy * iz));
+        start[cellof[i] + 1]++;
+    }
+    for (int64_t c = 0; c < nc; c++) start[c + 1] += start[c];
+    std::vector<int32_t> fill(start.begin(), start.end() - 1);
+    for (int64_t i = 0; i < n; i++) order[fill[cellof[i]]++] = (int32_t)i;
+    G.start = start.data(); G.order = order.data(); G.pos = pos;
+}
+
+extern "C" void vc_nn_harness(int64_t n, const double* pos, const double* bounds, int gx, int gy, int gz, int64_t m, const double* q,
+                              int64_t* idx, double* d2) {
+    VoroGrid G;
+    std::vector<int32_t> start, order;
+    build_grid(n, pos, bounds, gx, gy, gz, G, start, order);
+    for (int64_t k = 0; k < m; k++) idx[k] = nearest_site_of(G, q[3 * k], q[3 * k + 1], q[3 * k + 2], d2 + k) + 1;
+}
+
 extern "C" int vc_harness(int64_t n, const double* pos, const double* bounds, int gx, int gy, int gz, int64_t* nbr, int64_t ld,
                           int32_t* status) {
     VoroGrid G;

@@ -89,6 +89,7 @@ PROTOTYPES = {
                                              C.c_double, C.c_int32, vrt_iter_cb, C.c_void_p, P, P, C.POINTER(vrt_result)]),
     "vrt_voronoi_neighbours": (C.c_int, [C.c_int64, P, P, P, C.c_int64, c_int64_p]),
     "vrt_trilinear": (C.c_int, [C.c_int64, C.c_int64, C.c_int64, P, P, P, P, C.c_int64, P, P]),
+    "vrt_nearest_site": (C.c_int, [C.c_int64, P, P, C.c_int64, P, P, P]),
     "vrt_regular_grid_create": (C.c_int, [C.c_int64, C.c_int64, C.c_int64, P, P, P, C.POINTER(C.c_void_p)]),
     "vrt_regular_release_workspace": (C.c_int, []),
     "vrt_solver_create_line": (C.c_int, [C.c_void_p, C.POINTER(vrt_line), P, C.POINTER(vrt_site_data),

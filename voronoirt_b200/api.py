@@ -88,6 +88,34 @@ def voronoi_neighbours(positions, z_min, z_max, x_min, x_max, y_min, y_max):
     return np.asfortranarray(nbr[:, :need.value])
 
 
+def nearest_site(positions, bounds, points):
+    """nn(KDTree(positions), p) for every column of points (3, m) (src/voronoi_utils.jl:441-444) -> (idx 1-based (m,), dist (m,))"""
+    pos, q = _f(positions), _f(points)
+    b = np.ascontiguousarray(bounds, dtype=np.float64)
+    m = q.shape[1]
+    idx = np.zeros(m, dtype=np.int64)
+    dist = np.zeros(m)
+    check(lib().vrt_nearest_site(pos.shape[1], _ptr(pos), _ptr(b), m, _ptr(q), _ptr(idx), _ptr(dist)))
+    return idx, dist
+
+
+def Voronoi_to_Raster(sites, z, x, y, *fields):
+    """The resampling core of src/voronoi_utils.jl:407-471: nearest site of every raster point (z[k], x[i], y[j]), then the
+    gathers.  fields: per-site arrays (n,) or (nλ, n) -> rasters (nz, nx, ny) or (nλ, nz, nx, ny); returns (idx, *rasters)."""
+    z, x, y = (np.asarray(a, dtype=np.float64) for a in (z, x, y))
+    Z, X, Y = np.meshgrid(z, x, y, indexing="ij")
+    pts = np.asfortranarray(np.stack([Z.ravel(order="F"), X.ravel(order="F"), Y.ravel(order="F")]))
+    b = [sites.z_min, sites.z_max, sites.x_min, sites.x_max, sites.y_min, sites.y_max]
+    idx, _ = nearest_site(sites.positions, b, pts)
+    shape = (len(z), len(x), len(y))
+    out = []
+    for f in fields:
+        f = np.asarray(f)
+        g = f[..., idx - 1]
+        out.append(g.reshape(f.shape[:-1] + shape, order="F"))
+    return (idx.reshape(shape, order="F"),) + tuple(out)
+
+
 def trilinear(positions, atmos, vals):
     """src/functions.jl:207-248 broadcast over the sites: positions (3, n) rows (z, x, y), vals (nz, nx, ny) -> (n,)"""
     pos = _f(positions)

@@ -66,8 +66,60 @@ __global__ void k_vt_emit(int64_t n, int64_t ld, const int32_t* __restrict__ row
     nbr[idx] = c == 0 ? cnt : (c <= cnt && c < VT_CAP ? rows[i * VT_CAP + c] : 0);
 }
 
-struct MaxStatus {
-    int32_t max_cnt, bad;
+__global__ void k_vt_nearest(int64_t m, VoroGrid G, const double* __restrict__ q, int64_t* __restrict__ idx, double* __restrict__ dist) {
+    const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (k >= m) return;
+    double d2;
+    const int64_t j = nearest_site_of(G, q[3 * k], q[3 * k + 1], q[3 * k + 2], &d2);
+    idx[k] = j + 1;
+    if (dist) dist[k] = __dsqrt_rn(d2);
+}
+
+// the uniform search grid over the sites: cell of every site, CUB radix sort by cell, cell offsets
+struct SearchGrid {
+    VoroGrid G;
+    DevBuf<double> dpos;
+    DevBuf<int32_t> cell, cell_sorted, iota, order, start;
+    int build(const char* who, int64_t n, const double* positions, const double* bounds, double sites_per_cell) {
+        double hb[6];
+        VRT_CUDA(cudaMemcpy(hb, bounds, sizeof(hb), cudaMemcpyDefault));
+        G.z0 = hb[0]; G.Lz = hb[1] - hb[0];
+        G.x0 = hb[2]; G.Lx = hb[3] - hb[2];
+        G.y0 = hb[4]; G.Ly = hb[5] - hb[4];
+        if (!(G.Lx > 0) || !(G.Ly > 0) || !(G.Lz > 0)) {
+            set_error("%s: empty box", who);
+            return VRT_E_INVALID;
+        }
+        // near-cubic search cells
+        const double h = cbrt(G.Lx * G.Ly * G.Lz * sites_per_cell / (double)n);
+        auto cells = [&](double L) { return (int)std::max<int64_t>(1, std::min<int64_t>(1024, llround(L / h))); };
+        G.gx = cells(G.Lx); G.gy = cells(G.Ly); G.gz = cells(G.Lz);
+        G.hx = G.Lx / G.gx; G.hy = G.Ly / G.gy; G.hz = G.Lz / G.gz;
+        const int64_t nc = (int64_t)G.gx * G.gy * G.gz;
+        const double* pos = positions;
+        if (!is_device_ptr(positions)) {
+            VRT_TRY(dpos.alloc((size_t)3 * n));
+            VRT_CUDA(cudaMemcpy(dpos.p, positions, sizeof(double) * 3 * (size_t)n, cudaMemcpyHostToDevice));
+            pos = dpos.p;
+        }
+        VRT_TRY(cell.alloc(n)); VRT_TRY(cell_sorted.alloc(n)); VRT_TRY(iota.alloc(n)); VRT_TRY(order.alloc(n));
+        VRT_TRY(start.alloc(nc + 1));
+        const int bs = 256;
+        k_vt_cell_index<<<(unsigned)((n + bs - 1) / bs), bs>>>(n, pos, G, cell.p, iota.p);
+        VRT_CUDA(cudaGetLastError());
+        size_t tmp_bytes = 0;
+        int bits = 1;
+        while (((int64_t)1 << bits) < nc) bits++;
+        VRT_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, cell.p, cell_sorted.p, iota.p, order.p, (int)n, 0, bits));
+        DevBuf<char> tmp;
+        VRT_TRY(tmp.alloc(tmp_bytes));
+        VRT_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, cell.p, cell_sorted.p, iota.p, order.p, (int)n, 0, bits));
+        k_vt_cell_start<<<(unsigned)((n + 1 + bs - 1) / bs), bs>>>(n, nc, cell_sorted.p, start.p);
+        VRT_CUDA(cudaGetLastError());
+        VRT_CUDA(cudaDeviceSynchronize());   // `tmp` goes out of scope
+        G.start = start.p; G.order = order.p; G.pos = pos;
+        return VRT_OK;
+    }
 };
 
 __global__ void k_vt_reduce(int64_t n, const int32_t* __restrict__ rows, const int32_t* __restrict__ status, int32_t* __restrict__ out) {
@@ -94,53 +146,17 @@ extern "C" int vrt_voronoi_neighbours(int64_t n, const double* positions, const 
         set_error("vrt_voronoi_neighbours: no CUDA device (this library has no CPU path)");
         return VRT_E_CUDA;
     }
-    double hb[6];
-    VRT_CUDA(cudaMemcpy(hb, bounds, sizeof(hb), cudaMemcpyDefault));
-    VoroGrid G;
-    G.z0 = hb[0]; G.Lz = hb[1] - hb[0];
-    G.x0 = hb[2]; G.Lx = hb[3] - hb[2];
-    G.y0 = hb[4]; G.Ly = hb[5] - hb[4];
-    if (!(G.Lx > 0) || !(G.Ly > 0) || !(G.Lz > 0)) {
-        set_error("vrt_voronoi_neighbours: empty box");
-        return VRT_E_INVALID;
-    }
-    // near-cubic search cells with about four sites each
-    const double h = cbrt(G.Lx * G.Ly * G.Lz * 4.0 / (double)n);
-    auto cells = [&](double L) { return (int)std::max<int64_t>(1, std::min<int64_t>(1024, llround(L / h))); };
-    G.gx = cells(G.Lx); G.gy = cells(G.Ly); G.gz = cells(G.Lz);
-    G.hx = G.Lx / G.gx; G.hy = G.Ly / G.gy; G.hz = G.Lz / G.gz;
-    const int64_t nc = (int64_t)G.gx * G.gy * G.gz;
-
-    DevBuf<double> dpos;
-    const double* pos = positions;
-    if (!is_device_ptr(positions)) {
-        VRT_TRY(dpos.alloc((size_t)3 * n));
-        VRT_CUDA(cudaMemcpy(dpos.p, positions, sizeof(double) * 3 * (size_t)n, cudaMemcpyHostToDevice));
-        pos = dpos.p;
-    }
-    DevBuf<int32_t> cell, cell_sorted, iota, order, start, rows, status, red;
-    VRT_TRY(cell.alloc(n)); VRT_TRY(cell_sorted.alloc(n)); VRT_TRY(iota.alloc(n)); VRT_TRY(order.alloc(n));
-    VRT_TRY(start.alloc(nc + 1)); VRT_TRY(rows.alloc((size_t)n * VT_CAP)); VRT_TRY(status.alloc(n)); VRT_TRY(red.alloc(2));
     cudaEvent_t e0, e1;
     VRT_CUDA(cudaEventCreate(&e0));
     VRT_CUDA(cudaEventCreate(&e1));
     struct EvGuard { cudaEvent_t a, b; ~EvGuard() { cudaEventDestroy(a); cudaEventDestroy(b); } } evg{e0, e1};
     VRT_CUDA(cudaEventRecord(e0));
+    SearchGrid SG;
+    VRT_TRY(SG.build("vrt_voronoi_neighbours", n, positions, bounds, 4.0));   // about four sites per cell
+    const VoroGrid& G = SG.G;
+    DevBuf<int32_t> rows, status, red;
+    VRT_TRY(rows.alloc((size_t)n * VT_CAP)); VRT_TRY(status.alloc(n)); VRT_TRY(red.alloc(2));
     const int bs = 256;
-    k_vt_cell_index<<<(unsigned)((n + bs - 1) / bs), bs>>>(n, pos, G, cell.p, iota.p);
-    VRT_CUDA(cudaGetLastError());
-    {
-        size_t tmp_bytes = 0;
-        int bits = 1;
-        while (((int64_t)1 << bits) < nc) bits++;
-        VRT_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, cell.p, cell_sorted.p, iota.p, order.p, (int)n, 0, bits));
-        DevBuf<char> tmp;
-        VRT_TRY(tmp.alloc(tmp_bytes));
-        VRT_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, cell.p, cell_sorted.p, iota.p, order.p, (int)n, 0, bits));
-    }
-    k_vt_cell_start<<<(unsigned)((n + 1 + bs - 1) / bs), bs>>>(n, nc, cell_sorted.p, start.p);
-    VRT_CUDA(cudaGetLastError());
-    G.start = start.p; G.order = order.p; G.pos = pos;
     k_vt_cells<<<(unsigned)((n + 127) / 128), 128>>>(n, G, rows.p, status.p);
     VRT_CUDA(cudaGetLastError());
     VRT_CUDA(cudaMemset(red.p, 0, sizeof(int32_t) * 2));
@@ -179,5 +195,40 @@ extern "C" int vrt_voronoi_neighbours(int64_t n, const double* positions, const 
     }
     VRT_CUDA(cudaDeviceSynchronize());
     g_last_stats = st;
+    return VRT_OK;
+}
+
+extern "C" int vrt_nearest_site(int64_t n, const double* positions, const double bounds[6], int64_t m, const double* points,
+                                int64_t* idx, double* dist) {
+    if (n <= 0 || !positions || !bounds || m <= 0 || !points || !idx || n >= ((int64_t)1 << 31)) {
+        set_error("vrt_nearest_site: bad arguments");
+        return VRT_E_INVALID;
+    }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        set_error("vrt_nearest_site: no CUDA device (this library has no CPU path)");
+        return VRT_E_CUDA;
+    }
+    SearchGrid SG;
+    VRT_TRY(SG.build("vrt_nearest_site", n, positions, bounds, 2.0));
+    DevBuf<double> dq, dd;
+    DevBuf<int64_t> di;
+    const double* q = points;
+    if (!is_device_ptr(points)) {
+        VRT_TRY(dq.alloc((size_t)3 * m));
+        VRT_CUDA(cudaMemcpy(dq.p, points, sizeof(double) * 3 * (size_t)m, cudaMemcpyHostToDevice));
+        q = dq.p;
+    }
+    int64_t* oi = idx;
+    double* od = dist;
+    const bool dev_i = is_device_ptr(idx), dev_d = dist && is_device_ptr(dist);
+    if (!dev_i) { VRT_TRY(di.alloc(m)); oi = di.p; }
+    if (dist && !dev_d) { VRT_TRY(dd.alloc(m)); od = dd.p; }
+    k_vt_nearest<<<(unsigned)((m + 127) / 128), 128>>>(m, SG.G, q, oi, od);
+    VRT_CUDA(cudaGetLastError());
+    if (!dev_i) VRT_CUDA(cudaMemcpy(idx, di.p, sizeof(int64_t) * (size_t)m, cudaMemcpyDeviceToHost));
+    if (dist && !dev_d) VRT_CUDA(cudaMemcpy(dist, dd.p, sizeof(double) * (size_t)m, cudaMemcpyDeviceToHost));
+    VRT_CUDA(cudaDeviceSynchronize());
     return VRT_OK;
 }

@@ -16,6 +16,7 @@
 // Host/device code: the CUDA kernel (tessellate.cu) and the CPU harness of the tests (tests/voronoi_harness.cpp, test
 // infrastructure only) compile this same file, so the geometry is validated against voro++'s lists without a GPU.
 #pragma once
+#include <math.h>
 #include <stdint.h>
 
 #ifdef __CUDACC__
@@ -229,6 +230,67 @@ VC_HD int voronoi_cell_of(const VoroGrid& G, int64_t n, int64_t i, ConvexCell& c
     }
     (void)n;
     return cell.faces(out, cap);
+}
+
+// Nearest site of a query point (z, x, y) in plain Euclidean distance, no periodic wrap — what `nn(KDTree(positions), p)`
+// returns in Voronoi_to_Raster (voronoi_utils.jl:442-444).  Ring search over the same grid; ties go to the smaller index.
+// Every product and sum of the squared distance is rounded separately so that a host evaluation gives the same argmin.
+VC_HD double vc_mul(double a, double b) {
+#ifdef __CUDA_ARCH__
+    return __dmul_rn(a, b);
+#else
+    return a * b;
+#endif
+}
+VC_HD double vc_add(double a, double b) {
+#ifdef __CUDA_ARCH__
+    return __dadd_rn(a, b);
+#else
+    return a + b;
+#endif
+}
+
+VC_HD int64_t nearest_site_of(const VoroGrid& G, double qz, double qx, double qy, double* d2_out) {
+    int ix0 = (int)floor((qx - G.x0) / G.hx), iy0 = (int)floor((qy - G.y0) / G.hy), iz0 = (int)floor((qz - G.z0) / G.hz);
+    const bool inside = ix0 >= 0 && ix0 < G.gx && iy0 >= 0 && iy0 < G.gy && iz0 >= 0 && iz0 < G.gz;
+    ix0 = ix0 < 0 ? 0 : (ix0 >= G.gx ? G.gx - 1 : ix0);
+    iy0 = iy0 < 0 ? 0 : (iy0 >= G.gy ? G.gy - 1 : iy0);
+    iz0 = iz0 < 0 ? 0 : (iz0 >= G.gz ? G.gz - 1 : iz0);
+    const double hmin = G.hx < G.hy ? (G.hx < G.hz ? G.hx : G.hz) : (G.hy < G.hz ? G.hy : G.hz);
+    const int rmax = (G.gx > G.gy ? (G.gx > G.gz ? G.gx : G.gz) : (G.gy > G.gz ? G.gy : G.gz));
+    double best = 1.0e300;
+    int64_t arg = -1;
+    for (int r = 0; r <= rmax; r++) {
+        // sites of ring r are at least (r-1)*hmin away from a query inside the grid
+        if (inside && r > 0 && arg >= 0) {
+            const double dmin = (r - 1) * hmin;
+            if (dmin * dmin > best) break;
+        }
+        for (int dz = -r; dz <= r; dz++) {
+            const int iz = iz0 + dz;
+            if (iz < 0 || iz >= G.gz) continue;
+            const bool zface = dz == -r || dz == r;
+            for (int dy = -r; dy <= r; dy++) {
+                const int iy = iy0 + dy;
+                if (iy < 0 || iy >= G.gy) continue;
+                const bool yface = dy == -r || dy == r;
+                const int step = (zface || yface) ? 1 : (2 * r > 0 ? 2 * r : 1);
+                for (int dx = -r; dx <= r; dx += step) {
+                    const int ix = ix0 + dx;
+                    if (ix < 0 || ix >= G.gx) continue;
+                    const int64_t c = ix + (int64_t)G.gx * (iy + (int64_t)G.gy * iz);
+                    for (int32_t k = G.start[c]; k < G.start[c + 1]; k++) {
+                        const int64_t j = G.order[k];
+                        const double ez = G.pos[3 * j] - qz, ex = G.pos[3 * j + 1] - qx, ey = G.pos[3 * j + 2] - qy;
+                        const double d2 = vc_add(vc_add(vc_mul(ez, ez), vc_mul(ex, ex)), vc_mul(ey, ey));
+                        if (d2 < best || (d2 == best && j < arg)) { best = d2; arg = j; }
+                    }
+                }
+            }
+        }
+    }
+    if (d2_out) *d2_out = best;
+    return arg;
 }
 
 }  // namespace vrt
