@@ -1,6 +1,8 @@
 /*
  * vrt.h — C ABI of libvrt.so, the B200-native (sm_100a) short-characteristics formal solver and
- * Lambda-iteration engine for VoronoiRT's irregular-grid path.
+ * Lambda-iteration engine for VoronoiRT's irregular-grid path, plus the rows either side of it that SURVEY.md §8(f)
+ * ranks next: the regular-grid comparison solver, the Voronoi neighbour generation, site initialisation and the
+ * nearest-site query of the raster resampling.
  *
  * Every entry point replaces one Julia function of the reference (cited as file:line into the
  * reference tree).  The reference has no FFI of its own: its boundary is the set of Julia functions
@@ -29,7 +31,7 @@
 extern "C" {
 #endif
 
-#define VRT_ABI_VERSION 2
+#define VRT_ABI_VERSION 3   /* 3: regular-grid entries, native tessellation, trilinear, nearest site (additions only) */
 
 enum {
     VRT_OK = 0,
