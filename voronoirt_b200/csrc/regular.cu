@@ -304,6 +304,7 @@ __global__ void __launch_bounds__(MAXT) k_reg_rec(RegPlane P, int n_sweeps, cons
 // vrt_regular_release_workspace().  S and alpha are held once per internal layout (j = x and j = y).
 struct RegWorkspace {
     int device = -1;
+    uint64_t token = 0;   // changes whenever an entry point writes the S / alpha buffers (see regular_dir_accumulate)
     DevBuf<double> dS[2], dA[2], dI, stage, stage0, cA, cB, cC, dx, dy, dJ;
     DevBuf<unsigned long long> diff_bits;
     DevBuf<int> diff_nan;
@@ -311,6 +312,7 @@ struct RegWorkspace {
         return 8 * (dS[0].n + dS[1].n + dA[0].n + dA[1].n + dI.n + stage.n + stage0.n + cA.n + cB.n + cC.n + dx.n + dy.n + dJ.n);
     }
     void release_arrays() {   // before a grow: the large buffers only
+        token++;
         for (int i = 0; i < 2; i++) { dS[i].release(); dA[i].release(); }
         dI.release(); stage.release(); stage0.release(); cA.release(); cB.release(); cC.release(); dJ.release();
     }
@@ -568,6 +570,7 @@ int reg_mean_intensity(const char* who, const RegGeom& G, RegWorkspace& W, const
     }
     EvPair ev;
     VRT_TRY(ev.create());
+    W.token++;   // the S / alpha buffers are about to be overwritten
     for (int64_t l0 = 0; l0 < nlam; l0 += lc) {
         const int64_t n_l = std::min<int64_t>(lc, nlam - l0);
         bool have_S[2] = {false, false}, have_a_local[2] = {false, false};
@@ -687,7 +690,7 @@ int regular_dir_layout(const vrt_grid* g, const double k[3], int* layout) {
 
 int regular_dir_accumulate(const vrt_grid* g, const double k[3], int down, int n_sweeps, int64_t n_l, const double* S, int64_t S_ld,
                            int64_t S_l0, const double* alpha, int64_t a_ld, int64_t a_l0, const double* I0, double* J, int64_t J_ld,
-                           int64_t J_l0, double w, int accumulate, bool have_S[2], SweepStats* st) {
+                           int64_t J_l0, double w, int accumulate, bool have_S[2], uint64_t* token, SweepStats* st) {
     const char* who = "regular solver";
     RegGeom G;
     VRT_TRY(reg_geom_of(g, &G));
@@ -701,6 +704,9 @@ int regular_dir_accumulate(const vrt_grid* g, const double k[3], int down, int n
     // one buffer each for S and alpha (slot 0), whatever the layout: the caller groups its directions by layout, so S is
     // laid out twice per wavelength chunk, and the second slot's 2 volumes buy wider chunks instead
     const size_t need_vol = G.vol * n_l;
+    // the workspace is shared by every regular-grid entry of the process: S laid out by an earlier call of this function
+    // is only trusted when nobody wrote the buffers since (the caller carries the token from direction to direction)
+    if (*token != W.token) have_S[0] = have_S[1] = false;
     if (W.dI.n < need_vol || W.dS[0].n < need_vol || W.dA[0].n < need_vol || W.dS[1].p || W.dA[1].p) {
         W.release_arrays();
         have_S[0] = have_S[1] = false;
@@ -713,7 +719,9 @@ int regular_dir_accumulate(const vrt_grid* g, const double k[3], int down, int n
         VRT_TRY(reg_load(G, S, true, G.nz, S_ld, S_l0, n_l, lay, W.dS[0].p, W.stage, st));
         have_S[lay] = true;
         have_S[1 - lay] = false;
+        W.token++;
     }
+    *token = W.token;
     VRT_TRY(reg_load(G, alpha, true, G.nz, a_ld, a_l0, n_l, lay, W.dA[0].p, W.stage, st));
     double* pl = W.dI.p + G.plane * n_l * (down ? G.nz - 1 : 0);
     if (I0) VRT_TRY(reg_load(G, I0, true, 1, n_l, 0, n_l, lay, pl, W.stage0, st));
@@ -805,6 +813,7 @@ extern "C" int vrt_regular_formal_solve(int64_t nz, int64_t nx, int64_t ny, cons
     std::vector<int32_t> branch(nz, 0);
     EvPair ev;
     VRT_TRY(ev.create());
+    W.token++;   // the S / alpha buffers are about to be overwritten
     for (int64_t l0 = 0; l0 < nlam; l0 += lc) {
         const int64_t n_l = std::min<int64_t>(lc, nlam - l0);
         VRT_TRY(reg_load(G, S, dev_S, nz, nlam, l0, n_l, lay, W.dS[lay].p, W.stage, &stats));

@@ -703,6 +703,7 @@ static int mean_intensity_internal(vrt_solver* s, SweepStats* stats, double* t_o
         for (int64_t l0 = 0; l0 < s->nlam; l0 += s->lc) {
             const int64_t lc = std::min(s->lc, s->nlam - l0);
             bool have_S[2] = {false, false};
+            uint64_t ws_token = 0;
             // directions grouped by the internal layout they are solved in (S is then laid out twice per chunk, not per
             // direction); J therefore sums the directions in that order, not in the order of the quadrature file
             std::vector<int> order;
@@ -742,7 +743,7 @@ static int mean_intensity_internal(vrt_solver* s, SweepStats* stats, double* t_o
                     I0 = s->I_p[0];
                 }
                 VRT_TRY(regular_dir_accumulate(s->g, s->qk[d].data(), s->qdown[d], s->cfg.n_sweeps, lc, s->S.p, s->nlam, l0, alpha, a_ld, 0,
-                                               I0, s->J.p, s->nlam, l0, s->qw[d], oi > 0, have_S, stats));
+                                               I0, s->J.p, s->nlam, l0, s->qw[d], oi > 0, have_S, &ws_token, stats));
                 if (s->is_line) {
                     float ms = 0;
                     VRT_CUDA(cudaEventElapsedTime(&ms, e0, e1));

@@ -183,10 +183,11 @@ int permute_rows(const double* src, double* dst, const int32_t* map, int64_t n, 
 extern thread_local SweepStats g_last_stats;
 // regular.cu: one direction of J_λ_regular on DEVICE arrays in the caller's [cell][λ] layout (ld = wavelengths per cell,
 // l0 = first wavelength of the chunk): J[.., l0:l0+n_l] (+)= w * I.  I0: [nx*ny][n_l] boundary plane or nullptr (zero).
-// have_S[layout] says whether S of this chunk is already laid out (cleared by the caller per chunk / per new S).
+// have_S[layout] says whether S of this chunk is already laid out (cleared by the caller per chunk / per new S); token is the
+// caller's copy of the workspace generation: S is laid out again when another entry point wrote the shared buffers in between.
 int regular_dir_accumulate(const vrt_grid* g, const double k[3], int down, int n_sweeps, int64_t n_l, const double* S, int64_t S_ld,
                            int64_t S_l0, const double* alpha, int64_t a_ld, int64_t a_l0, const double* I0, double* J, int64_t J_ld,
-                           int64_t J_l0, double w, int accumulate, bool have_S[2], SweepStats* st);
+                           int64_t J_l0, double w, int accumulate, bool have_S[2], uint64_t* token, SweepStats* st);
 // internal layout (0: j = y, 1: j = x) a direction is solved in; callers group their directions by it
 int regular_dir_layout(const vrt_grid* g, const double k[3], int* layout);
 // wavelengths per chunk that fit next to `extra_vols` more volumes per wavelength held by the caller
