@@ -160,6 +160,15 @@ int vrt_voronoi_neighbours(int64_t n, const double* positions, const double boun
 int vrt_trilinear(int64_t nz, int64_t nx, int64_t ny, const double* z, const double* x, const double* y,
                   const double* vals, int64_t n, const double* positions, double* out);
 
+/* rejection_sampling(n_sites, atmos, quantity) (functions.jl:79-121): candidates uniform in the box of the axes, accepted
+ * when trilinear(quantity) > U(min quantity, max quantity); positions 3 x n_sites rows (z, x, y).  The candidate stream is
+ * Philox4x32-10 with counters (site, trial) and key `seed` — reproducible and independent of the thread mapping, but not
+ * Julia's Xoshiro stream: the acceptance rule, and therefore the distribution of the sites, is what is kept.  A candidate
+ * exactly on a lower face of the box (where the reference would throw) counts as rejected.  mean_trials (optional)
+ * receives the average number of candidates per site. */
+int vrt_rejection_sampling(int64_t n_sites, int64_t nz, int64_t nx, int64_t ny, const double* z, const double* x, const double* y,
+                           const double* quantity, uint64_t seed, double* positions, double* mean_trials);
+
 /* Nearest site of each of m points (3 x m rows (z, x, y)): the `nn(KDTree(ustrip.(sites.positions)), p)` of the
  * Voronoi -> raster resampling (voronoi_utils.jl:441-444 and its variants :479-771): plain Euclidean distance, no periodic
  * wrap.  idx: 1-based site ids (ties go to the smaller id), dist (optional): the distances.  The gathers that follow in the

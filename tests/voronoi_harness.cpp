@@ -6,6 +6,7 @@
 #include <string.h>
 #include <vector>
 #include "../voronoirt_b200/csrc/voronoi_cell.cuh"
+#include "../voronoirt_b200/csrc/sampling.cuh"
 
 using namespace vrt;
 
@@ -74,5 +75,28 @@ extern "C" int vc_harness(int64_t n, const double* pos, const double* bounds, in
         if (cnt < 0 || cnt > ld - 1) bad++;
     }
     delete cell;
+    return bad;
+}
+
+extern "C" void vc_philox(uint32_t* ctr, uint32_t k0, uint32_t k1) { philox4x32_10(ctr, k0, k1); }
+
+extern "C" int64_t vc_sample_harness(int64_t n_sites, int64_t nz, int64_t nx, int64_t ny, const double* z, const double* x, const double* y,
+                                     const double* q, uint64_t seed, double q_min, double dq, double* pos) {
+    TriGrid T = {nz, nx, ny, z, x, y, q};
+    int64_t trials = 0;
+    for (int64_t i = 0; i < n_sites; i++) {
+        int64_t t = rejection_site(T, seed, i, q_min, dq, 1 << 20, pos + 3 * i);
+        if (t < 0) return -1;
+        trials += t;
+    }
+    return trials;
+}
+
+extern "C" int64_t vc_trilinear_harness(int64_t nz, int64_t nx, int64_t ny, const double* z, const double* x, const double* y, const double* v,
+                                        int64_t n, const double* pos, double* out) {
+    TriGrid T = {nz, nx, ny, z, x, y, v};
+    int64_t bad = 0;
+    for (int64_t k = 0; k < n; k++)
+        if (!trilinear_at(T, pos[3 * k], pos[3 * k + 1], pos[3 * k + 2], out + k)) { out[k] = NAN; bad++; }
     return bad;
 }

@@ -128,6 +128,19 @@ def trilinear(positions, atmos, vals):
     return out
 
 
+def rejection_sampling(n_sites, atmos, quantity, seed=2022):
+    """src/functions.jl:79-121 -> p_vec (3, n_sites) rows (z, x, y); quantity (nz, nx, ny) on the atmosphere axes"""
+    q = _f(quantity)
+    if q.shape != atmos.shape:
+        raise ValueError("quantity must be (nz, nx, ny)")
+    pos = np.zeros((3, int(n_sites)), order="F")
+    mean = C.c_double()
+    check(lib().vrt_rejection_sampling(int(n_sites), atmos.shape[0], atmos.shape[1], atmos.shape[2], _ptr(atmos.z), _ptr(atmos.x),
+                                       _ptr(atmos.y), _ptr(q), int(seed), _ptr(pos), C.byref(mean)))
+    rejection_sampling.mean_trials = mean.value
+    return pos
+
+
 def initialise(p_vec, atmos):
     """src/voronoi_utils.jl:687-708 -> (temperature, N_e, N_H, velocity_z, velocity_x, velocity_y) at the sites"""
     return tuple(trilinear(p_vec, atmos, f) for f in (atmos.temperature, atmos.electron_density, atmos.hydrogen_populations,
