@@ -176,6 +176,17 @@ int vrt_rejection_sampling(int64_t n_sites, int64_t nz, int64_t nx, int64_t ny, 
 int vrt_nearest_site(int64_t n, const double* positions, const double bounds[6], int64_t m, const double* points,
                      int64_t* idx, double* dist);
 
+/* The k nearest sites (1 <= k <= 8) of each point, ascending by distance: `knn(tree, p, n_k)` of
+ * Voronoi_to_Raster_inv_dist (voronoi_utils.jl:797-805, n_k = 2; inv_dist_itp :848-860 stays with the host).
+ * idx, dist: k x m column-major. */
+int vrt_nearest_sites(int64_t n, const double* positions, const double bounds[6], int64_t m, const double* points, int32_t k,
+                      int64_t* idx, double* dist);
+
+/* initialiseII (voronoi_utils.jl:716-770) for one field: the value at the nearest of the eight corners of the cell of the
+ * atmosphere grid that holds the site (corners in the reference's order, first minimum wins).  Arguments as vrt_trilinear. */
+int vrt_nearest_corner(int64_t nz, int64_t nx, int64_t ny, const double* z, const double* x, const double* y,
+                       const double* vals, int64_t n, const double* positions, double* out);
+
 /* Build the grid: layers from the bottom/top wall (_sort_by_layer_up/_down, voronoi_utils.jl:93-174),
  * stable sort permutations and reduce_layers offsets (:71-79,:253-269), unit Delaunay edge vectors
  * (calc_Delaunay_lines, :186-245).  bounds = {z_min,z_max,x_min,x_max,y_min,y_max}. */

@@ -159,3 +159,39 @@ def test_gpu_rejection_sampling_equals_the_host_evaluation(harness):
     ref, trials = harness_sample(harness, n, z, x, y, q, 99)
     assert np.array_equal(pos, ref)
     assert abs(V.rejection_sampling.mean_trials - trials / n) < 1e-9
+
+
+def numpy_nearest_corner(z, x, y, vals, pos):
+    """voronoi_utils.jl:727-760: corners in the order (idz, idx, idy), (idz, idx, idy+1), (idz, idx+1, idy), ...; argmin of euclidean"""
+    out = np.zeros(pos.shape[1])
+    for k in range(pos.shape[1]):
+        zm, xm, ym = pos[:, k]
+        iz, ix, iy = (np.searchsorted(a, v, side="left") - 1 for a, v in ((z, zm), (x, xm), (y, ym)))
+        best = None
+        for a in (0, 1):
+            for b in (0, 1):
+                for c in (0, 1):
+                    d = np.sqrt((z[iz + a] - zm) ** 2 + (x[ix + b] - xm) ** 2 + (y[iy + c] - ym) ** 2)
+                    if best is None or d < best[0]:
+                        best = (d, vals[iz + a, ix + b, iy + c])
+        out[k] = best[1]
+    return out
+
+
+def test_nearest_corner_core(harness):
+    z, x, y, vals, pos = problem(np.random.default_rng(12), n=1500)
+    harness.vc_corner_harness.restype = C.c_int64
+    out = np.zeros(pos.shape[1])
+    bad = harness.vc_corner_harness(C.c_int64(len(z)), C.c_int64(len(x)), C.c_int64(len(y)), ptr(z), ptr(x), ptr(y), ptr(vals),
+                                    C.c_int64(pos.shape[1]), ptr(np.ascontiguousarray(pos.T)), ptr(out))
+    assert bad == 0 and np.array_equal(out, numpy_nearest_corner(z, x, y, vals, pos))
+
+
+@pytest.mark.gpu
+def test_gpu_initialiseII():
+    import voronoirt_b200 as V
+    z, x, y, vals, pos = problem(np.random.default_rng(13), n=3000)
+    atm = V.Atmosphere(z, x, y, *(vals * s for s in (1.0, 2.0, 3.0, -1.0, 0.5, 7.0)))
+    ref = numpy_nearest_corner(z, x, y, vals, pos)
+    for s, got in zip((1.0, 2.0, 3.0, -1.0, 0.5, 7.0), V.initialiseII(pos, atm)):
+        assert np.array_equal(got, ref * s)

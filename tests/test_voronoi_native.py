@@ -157,3 +157,51 @@ def test_gpu_nearest_site_and_raster():
     want, _ = brute_force_nn(pos, np.stack([Z.ravel(), X.ravel(), Y.ravel()]))
     assert np.array_equal(ridx.ravel(), want)
     assert np.array_equal(Tg, T[ridx - 1]) and np.array_equal(Sg, S[:, ridx - 1]) and Sg.shape == (7, 9, 6, 5)
+
+
+def brute_force_knn(pos, q, k):
+    d = (pos.T[None, :, :] - q.T[:, None, :]) ** 2
+    d2 = (d[:, :, 0] + d[:, :, 1]) + d[:, :, 2]
+    idx = np.argsort(d2, axis=1, kind="stable")[:, :k]
+    return (idx + 1).T, np.sqrt(np.take_along_axis(d2, idx, axis=1)).T
+
+
+def test_k_nearest_sites_core_equals_brute_force(harness):
+    pos, gold, b = load_grid("grid_strat3000")
+    q = queries(b, 3000, np.random.default_rng(8))
+    k = 4
+    idx = np.zeros((q.shape[1], k), dtype=np.int64)
+    d2 = np.zeros((q.shape[1], k))
+    p = np.ascontiguousarray(pos.T)
+    qq = np.ascontiguousarray(q.T)
+    harness.vc_knn_harness(C.c_int64(pos.shape[1]), p.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p), 8, 8, 13, C.c_int64(q.shape[1]),
+                           qq.ctypes.data_as(C.c_void_p), k, idx.ctypes.data_as(C.c_void_p), d2.ctypes.data_as(C.c_void_p))
+    ref, dist = brute_force_knn(pos, q, k)
+    assert np.array_equal(idx.T, ref) and np.array_equal(np.sqrt(d2).T, dist)
+
+
+@pytest.mark.gpu
+def test_gpu_k_nearest_and_inverse_distance_raster():
+    import voronoirt_b200 as V
+    pos, gold, b = load_grid("grid_strat3000")
+    q = queries(b, 3000, np.random.default_rng(9))
+    for k in (1, 2, 5):
+        idx, dist = V.nearest_sites(pos, b, q, k)
+        ref, rdist = brute_force_knn(pos, q, k)
+        assert np.array_equal(idx, ref) and np.array_equal(dist, rdist)
+    # Voronoi_to_Raster_inv_dist (voronoi_utils.jl:773-816, p = 1, n_k = 2) for the populations (n, 3)
+    n = pos.shape[1]
+    cell = V.read_cell(gold, n, pos, b[2], b[3], b[4], b[5])
+    rng = np.random.default_rng(10)
+    T = rng.uniform(4e3, 1e4, n)
+    pops = rng.uniform(1.0, 2.0, (n, 3))
+    sites = V.VoronoiSites(*cell, T, T, T, T, T, T, b[0], b[1], b[2], b[3], b[4], b[5], n)
+    z, x, y = np.linspace(b[0], b[1], 7), np.linspace(b[2], b[3], 5), np.linspace(b[4], b[5], 4)
+    grid = V.Voronoi_to_Raster_inv_dist(sites, z, x, y, pops)
+    assert grid.shape == (7, 5, 4, 3)
+    for (kk, ii, jj) in ((0, 0, 0), (3, 2, 1), (6, 4, 3)):
+        d = np.sqrt(((pos.T - np.array([z[kk], x[ii], y[jj]])) ** 2).sum(axis=1))
+        o = np.argsort(d, kind="stable")[:2]
+        inv = 1.0 / d[o]
+        want = (pops[o[0]] * inv[0] + pops[o[1]] * inv[1]) / (inv[0] + inv[1])
+        assert np.allclose(grid[kk, ii, jj], want, rtol=1e-14)

@@ -100,3 +100,23 @@ extern "C" int64_t vc_trilinear_harness(int64_t nz, int64_t nx, int64_t ny, cons
         if (!trilinear_at(T, pos[3 * k], pos[3 * k + 1], pos[3 * k + 2], out + k)) { out[k] = NAN; bad++; }
     return bad;
 }
+
+extern "C" void vc_knn_harness(int64_t n, const double* pos, const double* bounds, int gx, int gy, int gz, int64_t m, const double* q, int k,
+                               int64_t* idx, double* d2) {
+    VoroGrid G;
+    std::vector<int32_t> start, order;
+    build_grid(n, pos, bounds, gx, gy, gz, G, start, order);
+    for (int64_t p = 0; p < m; p++) {
+        int got = nearest_k_sites_of(G, n, k, q[3 * p], q[3 * p + 1], q[3 * p + 2], idx + p * k, d2 + p * k);
+        for (int t = 0; t < got; t++) idx[p * k + t] += 1;
+    }
+}
+
+extern "C" int64_t vc_corner_harness(int64_t nz, int64_t nx, int64_t ny, const double* z, const double* x, const double* y, const double* v,
+                                     int64_t n, const double* pos, double* out) {
+    TriGrid T = {nz, nx, ny, z, x, y, v};
+    int64_t bad = 0;
+    for (int64_t k = 0; k < n; k++)
+        if (!nearest_corner_at(T, pos[3 * k], pos[3 * k + 1], pos[3 * k + 2], out + k)) { out[k] = NAN; bad++; }
+    return bad;
+}

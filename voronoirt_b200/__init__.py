@@ -9,10 +9,10 @@ host-side mirror of the Julia interface.  There is no CPU fallback.
 """
 from .api import (Atmosphere, J_lambda_regular, J_λ_regular, Lambda_regular, Λ_regular, Delaunay_downII, Delaunay_upII, J_lambda_voronoi, J_λ_voronoi, Lambda_voronoi, Solver,  # noqa: F401
                   VoronoiSites, calculate_R, direction, get_revised_populations, quadrature_path, read_cell,
-                  read_neighbours, read_quadrature, regular_release_workspace, short_characteristics_down, voronoi_neighbours, trilinear, initialise, nearest_site, Voronoi_to_Raster, rejection_sampling, short_characteristics_up, voro,
+                  read_neighbours, read_quadrature, regular_release_workspace, short_characteristics_down, voronoi_neighbours, trilinear, initialise, nearest_site, nearest_sites, Voronoi_to_Raster, Voronoi_to_Raster_inv_dist, initialiseII, rejection_sampling, short_characteristics_up, voro,
                   write_arrays, Λ_voronoi)
 from .atom import B_λ, HydrogenicLine, LTE_populations, test_atom  # noqa: F401
 
-__all__ = ["Atmosphere", "J_λ_regular", "J_lambda_regular", "Λ_regular", "Lambda_regular", "short_characteristics_up", "short_characteristics_down", "regular_release_workspace", "voronoi_neighbours", "trilinear", "initialise", "nearest_site", "Voronoi_to_Raster", "rejection_sampling", "Delaunay_downII", "Delaunay_upII", "J_lambda_voronoi", "J_λ_voronoi", "Lambda_voronoi", "Solver", "VoronoiSites",
+__all__ = ["Atmosphere", "J_λ_regular", "J_lambda_regular", "Λ_regular", "Lambda_regular", "short_characteristics_up", "short_characteristics_down", "regular_release_workspace", "voronoi_neighbours", "trilinear", "initialise", "nearest_site", "nearest_sites", "Voronoi_to_Raster", "Voronoi_to_Raster_inv_dist", "initialiseII", "rejection_sampling", "Delaunay_downII", "Delaunay_upII", "J_lambda_voronoi", "J_λ_voronoi", "Lambda_voronoi", "Solver", "VoronoiSites",
            "calculate_R", "direction", "get_revised_populations", "quadrature_path", "read_cell", "read_neighbours",
            "read_quadrature", "voro", "write_arrays", "Λ_voronoi", "B_λ", "HydrogenicLine", "LTE_populations", "test_atom"]

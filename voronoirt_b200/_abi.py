@@ -91,6 +91,8 @@ PROTOTYPES = {
     "vrt_trilinear": (C.c_int, [C.c_int64, C.c_int64, C.c_int64, P, P, P, P, C.c_int64, P, P]),
     "vrt_nearest_site": (C.c_int, [C.c_int64, P, P, C.c_int64, P, P, P]),
     "vrt_rejection_sampling": (C.c_int, [C.c_int64, C.c_int64, C.c_int64, C.c_int64, P, P, P, P, C.c_uint64, P, c_double_p]),
+    "vrt_nearest_sites": (C.c_int, [C.c_int64, P, P, C.c_int64, P, C.c_int32, P, P]),
+    "vrt_nearest_corner": (C.c_int, [C.c_int64, C.c_int64, C.c_int64, P, P, P, P, C.c_int64, P, P]),
     "vrt_regular_grid_create": (C.c_int, [C.c_int64, C.c_int64, C.c_int64, P, P, P, C.POINTER(C.c_void_p)]),
     "vrt_regular_release_workspace": (C.c_int, []),
     "vrt_solver_create_line": (C.c_int, [C.c_void_p, C.POINTER(vrt_line), P, C.POINTER(vrt_site_data),

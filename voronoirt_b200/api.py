@@ -116,6 +116,51 @@ def Voronoi_to_Raster(sites, z, x, y, *fields):
     return (idx.reshape(shape, order="F"),) + tuple(out)
 
 
+def nearest_sites(positions, bounds, points, k):
+    """knn(KDTree(positions), p, k) for every column of points (3, m) -> (idx (k, m) 1-based, dist (k, m)), ascending"""
+    pos, q = _f(positions), _f(points)
+    b = np.ascontiguousarray(bounds, dtype=np.float64)
+    m = q.shape[1]
+    idx = np.zeros((k, m), dtype=np.int64, order="F")
+    dist = np.zeros((k, m), order="F")
+    check(lib().vrt_nearest_sites(pos.shape[1], _ptr(pos), _ptr(b), m, _ptr(q), int(k), _ptr(idx), _ptr(dist)))
+    return idx, dist
+
+
+def Voronoi_to_Raster_inv_dist(sites, z, x, y, values, p=1.0, n_k=2):
+    """The resampling core of src/voronoi_utils.jl:773-816: inverse-distance interpolation (inv_dist_itp, :848-860) over the
+    n_k nearest sites of every raster point.  values (n,) or (n, c) -> raster (nz, nx, ny) or (nz, nx, ny, c)."""
+    z, x, y = (np.asarray(a, dtype=np.float64) for a in (z, x, y))
+    Z, X, Y = np.meshgrid(z, x, y, indexing="ij")
+    pts = np.asfortranarray(np.stack([Z.ravel(order="F"), X.ravel(order="F"), Y.ravel(order="F")]))
+    b = [sites.z_min, sites.z_max, sites.x_min, sites.x_max, sites.y_min, sites.y_max]
+    idx, dist = nearest_sites(sites.positions, b, pts, n_k)
+    vals = np.asarray(values, dtype=np.float64)
+    v2 = vals.reshape(vals.shape[0], -1)
+    avg = np.zeros(pts.shape[1])
+    f = np.zeros((pts.shape[1], v2.shape[1]))
+    for t in range(n_k):                                   # the loop of inv_dist_itp, in its order
+        inv = 1.0 / dist[t] ** p
+        avg = avg + inv
+        f = f + v2[idx[t] - 1] * inv[:, None]
+    f = f / avg[:, None]
+    shape = (len(z), len(x), len(y))
+    return f.reshape(shape + vals.shape[1:], order="F") if vals.ndim > 1 else f[:, 0].reshape(shape, order="F")
+
+
+def initialiseII(p_vec, atmos):
+    """src/voronoi_utils.jl:716-770: nearest-corner values of the six atmosphere fields at the sites"""
+    pos = _f(p_vec)
+    out = []
+    for fld in (atmos.temperature, atmos.electron_density, atmos.hydrogen_populations, atmos.velocity_z, atmos.velocity_x, atmos.velocity_y):
+        v = _f(fld)
+        o = np.zeros(pos.shape[1])
+        check(lib().vrt_nearest_corner(atmos.shape[0], atmos.shape[1], atmos.shape[2], _ptr(atmos.z), _ptr(atmos.x), _ptr(atmos.y), _ptr(v),
+                                       pos.shape[1], _ptr(pos), _ptr(o)))
+        out.append(o)
+    return tuple(out)
+
+
 def trilinear(positions, atmos, vals):
     """src/functions.jl:207-248 broadcast over the sites: positions (3, n) rows (z, x, y), vals (nz, nx, ny) -> (n,)"""
     pos = _f(positions)

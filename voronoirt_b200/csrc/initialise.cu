@@ -26,6 +26,17 @@ __global__ void k_trilinear(TriGrid T, int64_t n, const double* __restrict__ pos
     out[k] = v;
 }
 
+__global__ void k_nearest_corner(TriGrid T, int64_t n, const double* __restrict__ pos, double* __restrict__ out, int* __restrict__ n_outside) {
+    const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    double v;
+    if (!nearest_corner_at(T, pos[3 * k], pos[3 * k + 1], pos[3 * k + 2], &v)) {
+        v = nan("");
+        atomicAdd(n_outside, 1);
+    }
+    out[k] = v;
+}
+
 __global__ void k_rejection_sampling(TriGrid T, uint64_t seed, int64_t n, double q_min, double dq, int64_t max_trials,
                                      double* __restrict__ pos, unsigned long long* __restrict__ trials, int* __restrict__ n_failed) {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -63,16 +74,16 @@ struct TriDev {
 
 using namespace vrt;
 
-extern "C" int vrt_trilinear(int64_t nz, int64_t nx, int64_t ny, const double* z, const double* x, const double* y,
+static int interpolate_sites(const char* who, int mode, int64_t nz, int64_t nx, int64_t ny, const double* z, const double* x, const double* y,
                              const double* vals, int64_t n, const double* positions, double* out) {
     if (nz < 2 || nx < 2 || ny < 2 || !z || !x || !y || !vals || n <= 0 || !positions || !out) {
-        set_error("vrt_trilinear: bad arguments");
+        set_error("%s: bad arguments", who);
         return VRT_E_INVALID;
     }
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
         cudaGetLastError();
-        set_error("vrt_trilinear: no CUDA device (this library has no CPU path)");
+        set_error("%s: no CUDA device (this library has no CPU path)", who);
         return VRT_E_CUDA;
     }
     TriDev D;
@@ -93,17 +104,28 @@ extern "C" int vrt_trilinear(int64_t nz, int64_t nx, int64_t ny, const double* z
     }
     VRT_TRY(flag.alloc(1));
     VRT_CUDA(cudaMemset(flag.p, 0, sizeof(int)));
-    k_trilinear<<<(unsigned)((n + 255) / 256), 256>>>(D.T, n, pp, po, flag.p);
+    if (mode == 0) k_trilinear<<<(unsigned)((n + 255) / 256), 256>>>(D.T, n, pp, po, flag.p);
+    else k_nearest_corner<<<(unsigned)((n + 255) / 256), 256>>>(D.T, n, pp, po, flag.p);
     VRT_CUDA(cudaGetLastError());
     int outside = 0;
     VRT_CUDA(cudaMemcpy(&outside, flag.p, sizeof(int), cudaMemcpyDeviceToHost));
     if (!dev_out) VRT_CUDA(cudaMemcpy(out, dout.p, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost));
     VRT_CUDA(cudaDeviceSynchronize());
     if (outside > 0) {
-        set_error("vrt_trilinear: %d sites lie outside the atmosphere axes (the reference throws a BoundsError there); their values are NaN", outside);
+        set_error("%s: %d sites lie outside the atmosphere axes (the reference throws a BoundsError there); their values are NaN", who, outside);
         return VRT_E_INVALID;
     }
     return VRT_OK;
+}
+
+extern "C" int vrt_trilinear(int64_t nz, int64_t nx, int64_t ny, const double* z, const double* x, const double* y,
+                             const double* vals, int64_t n, const double* positions, double* out) {
+    return interpolate_sites("vrt_trilinear", 0, nz, nx, ny, z, x, y, vals, n, positions, out);
+}
+
+extern "C" int vrt_nearest_corner(int64_t nz, int64_t nx, int64_t ny, const double* z, const double* x, const double* y,
+                                  const double* vals, int64_t n, const double* positions, double* out) {
+    return interpolate_sites("vrt_nearest_corner", 1, nz, nx, ny, z, x, y, vals, n, positions, out);
 }
 
 extern "C" int vrt_rejection_sampling(int64_t n_sites, int64_t nz, int64_t nx, int64_t ny, const double* z, const double* x,

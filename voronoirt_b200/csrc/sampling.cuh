@@ -65,6 +65,24 @@ VC_HD bool trilinear_at(const TriGrid& T, double zm, double xm, double ym, doubl
     return true;
 }
 
+// initialiseII (voronoi_utils.jl:716-770): the value at the nearest of the eight corners of the enclosing cell, corners in
+// the reference's order (y fastest, then x, then z), distances as `euclidean` computes them, first minimum wins
+VC_HD bool nearest_corner_at(const TriGrid& T, double zm, double xm, double ym, double* out) {
+    const int64_t iz = tri_lower_corner(T.z, T.nz, zm), ix = tri_lower_corner(T.x, T.nx, xm), iy = tri_lower_corner(T.y, T.ny, ym);
+    if (iz < 0 || iz > T.nz - 2 || ix < 0 || ix > T.nx - 2 || iy < 0 || iy > T.ny - 2 || !(zm == zm) || !(xm == xm) || !(ym == ym)) return false;
+    double best = 0.0;
+    int64_t arg = -1;
+    for (int a = 0; a < 2; a++)
+        for (int b = 0; b < 2; b++)
+            for (int c = 0; c < 2; c++) {
+                const double ez = vc_sub(T.z[iz + a], zm), ex = vc_sub(T.x[ix + b], xm), ey = vc_sub(T.y[iy + c], ym);
+                const double d = sqrt(vc_add(vc_add(vc_mul(ez, ez), vc_mul(ex, ex)), vc_mul(ey, ey)));
+                if (arg < 0 || d < best) { best = d; arg = (iz + a) + T.nz * ((ix + b) + T.nx * (iy + c)); }
+            }
+    *out = T.vals[arg];
+    return true;
+}
+
 // Philox4x32-10 (Salmon, Moraes, Dror & Shaw 2011): counter-based, so site i's candidate stream does not depend on how
 // the sites are spread over threads.  (The reference draws from Julia's task-local Xoshiro stream, which cannot be
 // reproduced; what is kept is the acceptance rule and therefore the distribution.)

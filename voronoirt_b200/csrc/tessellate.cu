@@ -75,6 +75,19 @@ __global__ void k_vt_nearest(int64_t m, VoroGrid G, const double* __restrict__ q
     if (dist) dist[k] = __dsqrt_rn(d2);
 }
 
+__global__ void k_vt_nearest_k(int64_t n, int64_t m, int k, VoroGrid G, const double* __restrict__ q, int64_t* __restrict__ idx,
+                               double* __restrict__ dist) {
+    const int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (p >= m) return;
+    int64_t bi[VC_KMAX];
+    double bd[VC_KMAX];
+    const int got = nearest_k_sites_of(G, n, k, q[3 * p], q[3 * p + 1], q[3 * p + 2], bi, bd);
+    for (int t = 0; t < k; t++) {
+        idx[p * k + t] = t < got ? bi[t] + 1 : 0;
+        if (dist) dist[p * k + t] = t < got ? __dsqrt_rn(bd[t]) : nan("");
+    }
+}
+
 // the uniform search grid over the sites: cell of every site, CUB radix sort by cell, cell offsets
 struct SearchGrid {
     VoroGrid G;
@@ -229,6 +242,41 @@ extern "C" int vrt_nearest_site(int64_t n, const double* positions, const double
     VRT_CUDA(cudaGetLastError());
     if (!dev_i) VRT_CUDA(cudaMemcpy(idx, di.p, sizeof(int64_t) * (size_t)m, cudaMemcpyDeviceToHost));
     if (dist && !dev_d) VRT_CUDA(cudaMemcpy(dist, dd.p, sizeof(double) * (size_t)m, cudaMemcpyDeviceToHost));
+    VRT_CUDA(cudaDeviceSynchronize());
+    return VRT_OK;
+}
+
+extern "C" int vrt_nearest_sites(int64_t n, const double* positions, const double bounds[6], int64_t m, const double* points, int32_t k,
+                                 int64_t* idx, double* dist) {
+    if (n <= 0 || !positions || !bounds || m <= 0 || !points || !idx || n >= ((int64_t)1 << 31) || k < 1 || k > VC_KMAX) {
+        set_error("vrt_nearest_sites: bad arguments (1 <= k <= %d)", VC_KMAX);
+        return VRT_E_INVALID;
+    }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        set_error("vrt_nearest_sites: no CUDA device (this library has no CPU path)");
+        return VRT_E_CUDA;
+    }
+    SearchGrid SG;
+    VRT_TRY(SG.build("vrt_nearest_sites", n, positions, bounds, 2.0));
+    DevBuf<double> dq, dd;
+    DevBuf<int64_t> di;
+    const double* q = points;
+    if (!is_device_ptr(points)) {
+        VRT_TRY(dq.alloc((size_t)3 * m));
+        VRT_CUDA(cudaMemcpy(dq.p, points, sizeof(double) * 3 * (size_t)m, cudaMemcpyHostToDevice));
+        q = dq.p;
+    }
+    int64_t* oi = idx;
+    double* od = dist;
+    const bool dev_i = is_device_ptr(idx), dev_d = dist && is_device_ptr(dist);
+    if (!dev_i) { VRT_TRY(di.alloc((size_t)m * k)); oi = di.p; }
+    if (dist && !dev_d) { VRT_TRY(dd.alloc((size_t)m * k)); od = dd.p; }
+    k_vt_nearest_k<<<(unsigned)((m + 127) / 128), 128>>>(n, m, k, SG.G, q, oi, od);
+    VRT_CUDA(cudaGetLastError());
+    if (!dev_i) VRT_CUDA(cudaMemcpy(idx, di.p, sizeof(int64_t) * (size_t)m * k, cudaMemcpyDeviceToHost));
+    if (dist && !dev_d) VRT_CUDA(cudaMemcpy(dist, dd.p, sizeof(double) * (size_t)m * k, cudaMemcpyDeviceToHost));
     VRT_CUDA(cudaDeviceSynchronize());
     return VRT_OK;
 }

@@ -293,4 +293,59 @@ VC_HD int64_t nearest_site_of(const VoroGrid& G, double qz, double qx, double qy
     return arg;
 }
 
+// The k nearest sites (k <= VC_KMAX), ascending by (distance, index): `knn(tree, p, n_k)` of Voronoi_to_Raster_inv_dist
+// (voronoi_utils.jl:797-805; the reference does not sort its result, the inverse-distance sum does not depend on the order).
+constexpr int VC_KMAX = 8;
+
+VC_HD int nearest_k_sites_of(const VoroGrid& G, int64_t n, int k, double qz, double qx, double qy, int64_t* idx_out, double* d2_out) {
+    if (k > VC_KMAX) k = VC_KMAX;
+    if ((int64_t)k > n) k = (int)n;
+    int ix0 = (int)floor((qx - G.x0) / G.hx), iy0 = (int)floor((qy - G.y0) / G.hy), iz0 = (int)floor((qz - G.z0) / G.hz);
+    const bool inside = ix0 >= 0 && ix0 < G.gx && iy0 >= 0 && iy0 < G.gy && iz0 >= 0 && iz0 < G.gz;
+    ix0 = ix0 < 0 ? 0 : (ix0 >= G.gx ? G.gx - 1 : ix0);
+    iy0 = iy0 < 0 ? 0 : (iy0 >= G.gy ? G.gy - 1 : iy0);
+    iz0 = iz0 < 0 ? 0 : (iz0 >= G.gz ? G.gz - 1 : iz0);
+    const double hmin = G.hx < G.hy ? (G.hx < G.hz ? G.hx : G.hz) : (G.hy < G.hz ? G.hy : G.hz);
+    const int rmax = (G.gx > G.gy ? (G.gx > G.gz ? G.gx : G.gz) : (G.gy > G.gz ? G.gy : G.gz));
+    double bd[VC_KMAX];
+    int64_t bi[VC_KMAX];
+    int have = 0;
+    for (int r = 0; r <= rmax; r++) {
+        if (inside && r > 0 && have == k) {
+            const double dmin = (r - 1) * hmin;
+            if (dmin * dmin > bd[k - 1]) break;
+        }
+        for (int dz = -r; dz <= r; dz++) {
+            const int iz = iz0 + dz;
+            if (iz < 0 || iz >= G.gz) continue;
+            const bool zface = dz == -r || dz == r;
+            for (int dy = -r; dy <= r; dy++) {
+                const int iy = iy0 + dy;
+                if (iy < 0 || iy >= G.gy) continue;
+                const bool yface = dy == -r || dy == r;
+                const int step = (zface || yface) ? 1 : (2 * r > 0 ? 2 * r : 1);
+                for (int dx = -r; dx <= r; dx += step) {
+                    const int ix = ix0 + dx;
+                    if (ix < 0 || ix >= G.gx) continue;
+                    const int64_t c = ix + (int64_t)G.gx * (iy + (int64_t)G.gy * iz);
+                    for (int32_t q = G.start[c]; q < G.start[c + 1]; q++) {
+                        const int64_t j = G.order[q];
+                        const double ez = G.pos[3 * j] - qz, ex = G.pos[3 * j + 1] - qx, ey = G.pos[3 * j + 2] - qy;
+                        const double d2 = vc_add(vc_add(vc_mul(ez, ez), vc_mul(ex, ex)), vc_mul(ey, ey));
+                        if (have == k && !(d2 < bd[k - 1] || (d2 == bd[k - 1] && j < bi[k - 1]))) continue;
+                        int p = have < k ? have++ : k - 1;   // insertion into the sorted list
+                        while (p > 0 && (d2 < bd[p - 1] || (d2 == bd[p - 1] && j < bi[p - 1]))) {
+                            bd[p] = bd[p - 1]; bi[p] = bi[p - 1];
+                            p--;
+                        }
+                        bd[p] = d2; bi[p] = j;
+                    }
+                }
+            }
+        }
+    }
+    for (int p = 0; p < have; p++) { idx_out[p] = bi[p]; d2_out[p] = bd[p]; }
+    return have;
+}
+
 }  // namespace vrt
