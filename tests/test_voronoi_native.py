@@ -205,3 +205,25 @@ def test_gpu_k_nearest_and_inverse_distance_raster():
         inv = 1.0 / d[o]
         want = (pops[o[0]] * inv[0] + pops[o[1]] * inv[1]) / (inv[0] + inv[1])
         assert np.allclose(grid[kk, ii, jj], want, rtol=1e-14)
+
+
+def tiny_cases():
+    d = np.load(os.path.join(HERE, "golden", "tiny_voro.npz"))
+    return [(np.asfortranarray(d[f"pos_{c}"]), d[f"nbr_{c}"].astype(np.int64)) for c in range(int(d["n_cases"]))]
+
+
+def test_nearly_empty_periodic_boxes(harness):
+    """1..40 sites in the unit box (tests/make_tiny_golden.py): cells bounded by periodic images, also of the site itself
+    (voro++ then lists the site's own id); bisectors through cell edges must not become faces"""
+    b = np.array([0.0, 1.0, 0.0, 1.0, 0.0, 1.0])
+    for pos, gold in tiny_cases():
+        nbr, st, bad = run_harness(harness, pos, b)
+        assert bad == 0 and same_sets(nbr, gold), pos.shape
+
+
+@pytest.mark.gpu
+def test_gpu_nearly_empty_periodic_boxes():
+    import voronoirt_b200 as V
+    for pos, gold in tiny_cases():
+        nbr = V.voronoi_neighbours(pos, 0.0, 1.0, 0.0, 1.0, 0.0, 1.0)
+        assert same_sets(np.asarray(nbr), gold), pos.shape

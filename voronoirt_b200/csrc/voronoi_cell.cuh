@@ -121,9 +121,13 @@ struct ConvexCell {
 
     // clip by a x + b y + c z + d >= 0; returns true when the plane cuts the cell (it then stays as a face candidate)
     VC_HD bool clip(double a, double b, double c, double d, int64_t id) {
+        // a vertex counts as cut only when it is outside by more than a relative tolerance (voro++ does the same with its
+        // 1e-11): the bisector with a diagonal periodic image of a site of a nearly empty box passes exactly through an
+        // edge of the cell and must not become a zero-area face
+        const double tol = -1e-11 * d;
         int nrem = 0;
         for (int t = 0; t < nt; t++) {
-            const bool out = a * vx[t] + b * vy[t] + c * vz[t] + d < 0.0;
+            const bool out = a * vx[t] + b * vy[t] + c * vz[t] + d < tol;
             rem[t] = out ? 1 : 0;
             nrem += out ? 1 : 0;
         }
