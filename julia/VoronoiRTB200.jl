@@ -204,6 +204,51 @@ end
 # Λ_regular(ϵ, maxiter, atmos, line, quadrature, DATA; …) is Λ_voronoi above with `grid_of(sites)` replaced by
 # `regular_grid(atmos)`, `sites.*` by `atmos.*` and the results reshaped to (nλ, nz, nx, ny) / (nz, nx, ny, 3).
 
+# ---------------------------------------------------------------- site set-up and resampling (optional replacements)
+# NeighbourMatrix straight from the positions instead of write_arrays + voro++ + the parser of read_cell
+# (src/io.jl:8-40, rt_preprocessing/output_sites.cc, src/voronoi_utils.jl:42-70).  Same neighbour sets; the order inside a
+# row differs from voro++'s, and smallest_angle is order-dependent (see DESIGN.md §2).
+function voronoi_neighbours(positions::Matrix{<:Unitful.Length}, z_min, z_max, x_min, x_max, y_min, y_max)
+    pos = Float64.(ustrip.(u"m", positions))
+    n = size(pos, 2)
+    b = Float64.(ustrip.(u"m", [z_min, z_max, x_min, x_max, y_min, y_max]))
+    nbr = zeros(Int64, n, 64)
+    need = Ref{Int64}(0)
+    check(ccall((:vrt_voronoi_neighbours, libvrt), Cint, (Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Int64}, Int64, Ref{Int64}),
+                n, pos, b, nbr, 64, need))
+    return nbr[:, 1:need[]]
+end
+
+# trilinear over all sites (src/functions.jl:207-248); initialise (src/voronoi_utils.jl:687-708) is six of these
+function trilinear(p_vec::Matrix{<:Unitful.Length}, atmos, vals::Array{Float64,3})
+    pos = Float64.(ustrip.(u"m", p_vec))
+    z = Float64.(ustrip.(u"m", atmos.z)); x = Float64.(ustrip.(u"m", atmos.x)); y = Float64.(ustrip.(u"m", atmos.y))
+    out = Vector{Float64}(undef, size(pos, 2))
+    check(ccall((:vrt_trilinear, libvrt), Cint,
+                (Int64, Int64, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int64, Ptr{Float64}, Ptr{Float64}),
+                length(z), length(x), length(y), z, x, y, vals, size(pos, 2), pos, out))
+    return out
+end
+
+# rejection_sampling(n_sites, atmos, quantity) (src/functions.jl:79-121) with a reproducible Philox stream
+function rejection_sampling(n_sites::Int, atmos, quantity::Array{Float64,3}; seed::UInt64=UInt64(2022))
+    z = Float64.(ustrip.(u"m", atmos.z)); x = Float64.(ustrip.(u"m", atmos.x)); y = Float64.(ustrip.(u"m", atmos.y))
+    p_vec = Matrix{Float64}(undef, 3, n_sites)
+    check(ccall((:vrt_rejection_sampling, libvrt), Cint,
+                (Int64, Int64, Int64, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, UInt64, Ptr{Float64}, Ptr{Float64}),
+                n_sites, length(z), length(x), length(y), z, x, y, quantity, seed, p_vec, C_NULL))
+    return p_vec * u"m"
+end
+
+# idx, dist = nn(KDTree(positions), p) for all raster points at once (src/voronoi_utils.jl:441-444)
+function nearest_site(positions::Matrix{Float64}, bounds::Vector{Float64}, points::Matrix{Float64})
+    m = size(points, 2)
+    idx = Vector{Int64}(undef, m); dist = Vector{Float64}(undef, m)
+    check(ccall((:vrt_nearest_site, libvrt), Cint, (Int64, Ptr{Float64}, Ptr{Float64}, Int64, Ptr{Float64}, Ptr{Int64}, Ptr{Float64}),
+                size(positions, 2), positions, bounds, m, points, idx, dist))
+    return idx, dist
+end
+
 function readdlm_quadrature(fname)
     rows = [parse.(Float64, split(l)) for l in eachline(fname) if !isempty(strip(l))]
     return permutedims(hcat(rows...))
