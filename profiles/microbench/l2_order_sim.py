@@ -137,3 +137,29 @@ for cells_per_tile in (64, 256, 1024):
     mE = misses(trace(oE, P, 0), cap)
     print(f"E tiles of ~{cells_per_tile:4d} cells, upwind tiles first   misses per visit {mE / len(c):5.2f}   = {mE / algorithmic:4.2f} x algorithmic   "
           f"({viol} of {2 * len(c)} dependencies point against the order)")
+
+# F: the valid version of E: key = max(own (tile, level) key, key of the producers) — a topological order by construction
+for cells_per_tile in (256,):
+    ntile = max(1, int(round((n / cells_per_tile) ** (1 / 3))))
+    q = ((pos - pos.min(axis=1, keepdims=True)) / (np.ptp(pos, axis=1)[:, None] + 1e-300) * ntile).astype(np.int64).clip(0, ntile - 1)
+    tile = q[0] + ntile * (q[1] + ntile * q[2])
+    centre = (q + 0.5) / ntile * np.ptp(pos, axis=1)[:, None]
+    proj = -(kvec[:, None] * centre).sum(axis=0)
+    tkey = np.round(proj / np.ptp(proj) * 1e6).astype(np.int64) * (ntile ** 3) + tile
+    uniq, tord = np.unique(tkey, return_inverse=True)          # position of the cell's tile in the tile order
+    own = tord.astype(np.float64) * 1e3 + P["level"]            # (tile, level)
+    key = own.copy()
+    rank = P["rank"]
+    for cc in c[np.argsort(rank[c])]:                           # reference order: producers come first
+        for m in (0, 1):
+            uu = P["u"][cc, m]
+            if rank[uu] < rank[cc] and key[uu] >= key[cc]:
+                key[cc] = np.nextafter(key[uu], np.inf)
+    oF = c[np.lexsort((rank[c], key[c]))]
+    posn = np.full(n, -1, dtype=np.int64)
+    posn[oF] = np.arange(len(oF))
+    viol = sum(int((((rank[P["u"][oF, m]] < rank[oF]) & (posn[P["u"][oF, m]] >= 0)) & (posn[P["u"][oF, m]] > posn[oF])).sum()) for m in (0, 1))
+    mF = misses(trace(oF, P, 0), cap)
+    moved = int((key[c] != own[c]).sum())
+    print(f"F valid tile order (~{cells_per_tile} cells per tile)          misses per visit {mF / len(c):5.2f}   = {mF / algorithmic:4.2f} x algorithmic   "
+          f"({viol} violations, {moved} cells pushed behind a producer)")
