@@ -74,8 +74,6 @@ def run(theta, phi, cells_per_tile=64):
 
     # DAG level of every visit, in reference order (producers first)
     level = {}
-    for s_outer in (0,):
-        pass
     order_ref = [(c, s) for L in range(2, len(off)) for s in range(1, NS + 1) for c in processed[layer[processed] == L]]
     deps = {}
     for (c, s) in order_ref:
@@ -119,5 +117,6 @@ def run(theta, phi, cells_per_tile=64):
     return same
 
 
-ok = all(run(th, ph) for th, ph in ((152.7, 315.5), (67.2, 155.8), (101.8, 235.4), (27.3, 135.5)))
-sys.exit(0 if ok else 1)
+if __name__ == "__main__":
+    ok = all(run(th, ph) for th, ph in ((152.7, 315.5), (67.2, 155.8), (101.8, 235.4), (27.3, 135.5)))
+    sys.exit(0 if ok else 1)
