@@ -31,7 +31,8 @@
 extern "C" {
 #endif
 
-#define VRT_ABI_VERSION 3   /* 3: regular-grid entries, native tessellation, trilinear, nearest site (additions only) */
+#define VRT_ABI_VERSION 4   /* 3: regular-grid entries, native tessellation, trilinear, nearest site; 4: schedule release, in-library
+                               collectives, cell-sliced state, output file (additions only) */
 
 enum {
     VRT_OK = 0,
@@ -214,6 +215,10 @@ int vrt_grid_get_stencil(vrt_grid* g, const double k[3], double p,
  * n_steps = number of grid-wide dependent steps of the sweep program actually executed. */
 int vrt_grid_get_schedule(vrt_grid* g, const double k[3], int32_t down, int32_t n_sweeps, int32_t prune,
                           int32_t* cls, int32_t* sublevel, int32_t* stab, int64_t* n_steps, int64_t* n_visits);
+
+/* Frees the sweep programs the grid caches per (direction, n_sweeps, p, prune) — tens of bytes per cell and direction.
+ * Only when no solver created on this grid is alive (their programs are the cached ones); they are rebuilt on demand. */
+int vrt_grid_release_schedules(vrt_grid* g);
 
 /* ---------------------------------------------------------------- formal solver */
 

@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), f"libvrt.so does not export {n}"
     assert sorted(_abi.PROTOTYPES) == names, "voronoirt_b200/_abi.py and include/vrt.h declare different entry points"
-    assert _lib.lib().vrt_abi_version() == 3
+    assert _lib.lib().vrt_abi_version() == 4
 
 
 def test_struct_layouts_match_the_header():

@@ -80,6 +80,7 @@ PROTOTYPES = {
     "vrt_grid_get_delaunay_lines": (C.c_int, [C.c_void_p, P]),
     "vrt_grid_get_stencil": (C.c_int, [C.c_void_p, P, C.c_double, P, P, P, P]),
     "vrt_grid_get_schedule": (C.c_int, [C.c_void_p, P, C.c_int32, C.c_int32, C.c_int32, P, P, P, c_int64_p, c_int64_p]),
+    "vrt_grid_release_schedules": (C.c_int, [C.c_void_p]),
     "vrt_formal_solve": (C.c_int, [C.c_void_p, P, C.c_int32, C.c_double, C.c_int32, C.c_int64, P, P, P, P]),
     "vrt_regular_formal_solve": (C.c_int, [C.c_int64, C.c_int64, C.c_int64, P, P, P, P, C.c_int32, C.c_int32, C.c_int64,
                                            P, P, P, P, P]),

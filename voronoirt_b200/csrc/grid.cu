@@ -382,6 +382,7 @@ using namespace vrt;
 
 vrt_grid::~vrt_grid() {
     for (auto* s : cache) delete s;
+    vrt::sweep_timers_free(sweep_timers);
 }
 
 extern "C" {
@@ -490,6 +491,12 @@ int vrt_grid_get_stencil(vrt_grid* g, const double k[3], double p, int64_t* upwi
     return VRT_OK;
 }
 
+int vrt_grid_release_schedules(vrt_grid* g) {
+    if (!g) return VRT_E_INVALID;
+    schedule_cache_clear(g);
+    return VRT_OK;
+}
+
 int vrt_grid_get_schedule(vrt_grid* g, const double k[3], int32_t down, int32_t n_sweeps, int32_t prune,
                           int32_t* cls, int32_t* sublevel, int32_t* stab, int64_t* n_steps, int64_t* n_visits) {
     if (g && g->regular) {
@@ -497,9 +504,10 @@ int vrt_grid_get_schedule(vrt_grid* g, const double k[3], int32_t down, int32_t 
         return VRT_E_STATE;
     }
     if (!g || !k) return VRT_E_INVALID;
-    int rc = VRT_OK;
-    DirSchedule* sch = schedule_get(g, k, down, n_sweeps, 7.0, prune, 1, &rc);
-    if (!sch) return rc;
+    // built on request with the introspection arrays kept (the cached schedules of the solvers drop them)
+    DirSchedule* sch = nullptr;
+    VRT_TRY(schedule_build(g, k, down, n_sweeps, 7.0, prune, 1, order_config(g->n, 1), true, &sch));
+    struct Guard { DirSchedule* s; ~Guard() { delete s; } } guard{sch};
     const int64_t n = g->n;
     DevBuf<int32_t> tmp;
     VRT_TRY(tmp.alloc(2 * n));

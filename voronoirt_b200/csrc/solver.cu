@@ -494,8 +494,21 @@ struct vrt_solver {
     DevBuf<int> diff_nan;
     vrt_allreduce_fn allreduce = nullptr;
     void* allreduce_user = nullptr;
+    // CUDA events are created once and reused (no create/destroy per iteration, nothing to leak on an early return)
+    std::vector<cudaEvent_t> ev_pool;
+    size_t ev_used = 0;
+    int event(cudaEvent_t* e) {
+        if (ev_used == ev_pool.size()) {
+            cudaEvent_t n;
+            VRT_CUDA(cudaEventCreate(&n));
+            ev_pool.push_back(n);
+        }
+        *e = ev_pool[ev_used++];
+        return VRT_OK;
+    }
     ~vrt_solver() {
         for (auto* b : bufs) delete b;
+        for (auto e : ev_pool) cudaEventDestroy(e);
     }
 };
 
@@ -687,9 +700,11 @@ static int plan_buffers(vrt_solver* s) {
 static int mean_intensity_internal(vrt_solver* s, SweepStats* stats, double* t_opacity_ms, double* t_sweep_ms, bool scatter = false) {
     const int64_t n = s->n;
     VRT_TRY(plan_buffers(s));
+    s->ev_used = 0;
     cudaEvent_t e0, e1;
-    VRT_CUDA(cudaEventCreate(&e0));
-    VRT_CUDA(cudaEventCreate(&e1));
+    VRT_TRY(s->event(&e0));
+    VRT_TRY(s->event(&e1));
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> op_ev;   // opacity launches of the irregular path, resolved after the final sync
     float opacity_ms = 0;
     if (s->is_line) {
         k_gamma<<<nblocks(n, 256), 256>>>(n, s->ld, s->T.p, s->ne.p, s->pops.p, s->gamma.p);
@@ -753,8 +768,6 @@ static int mean_intensity_internal(vrt_solver* s, SweepStats* stats, double* t_o
         }
         if (s->nd == 0) VRT_CUDA(cudaMemset(s->J.p, 0, sizeof(double) * (size_t)n * s->nlam));
         VRT_CUDA(cudaDeviceSynchronize());
-        cudaEventDestroy(e0);
-        cudaEventDestroy(e1);
         if (t_opacity_ms) *t_opacity_ms = opacity_ms;
         if (t_sweep_ms) *t_sweep_ms = stats->sweep_ms;
         return VRT_OK;
@@ -790,7 +803,11 @@ static int mean_intensity_internal(vrt_solver* s, SweepStats* stats, double* t_o
                 stats->kernels += 1;
             }
             if (s->is_line) {
-                VRT_CUDA(cudaEventRecord(e0));
+                cudaEvent_t o0, o1;
+                VRT_TRY(s->event(&o0));
+                VRT_TRY(s->event(&o1));
+                op_ev.emplace_back(o0, o1);
+                VRT_CUDA(cudaEventRecord(o0));
                 {
                     const size_t shm = sizeof(double) * OP_TC * (size_t)((int)lc | 1);
                     const int grid = (int)std::min<int64_t>((n + OP_TC - 1) / OP_TC, 148 * 16);
@@ -798,25 +815,26 @@ static int mean_intensity_internal(vrt_solver* s, SweepStats* stats, double* t_o
                     k_opacity<<<grid, OP_THREADS, shm>>>(n, lc, s->lam_dev.p + s->l_begin + l0, s->ld, od, s->gamma.p, s->dD.p, s->vz.p,
                                                         s->vx.p, s->vy.p, s->pops.p, s->alpha_cont.p);
                 }
-                VRT_CUDA(cudaEventRecord(e1));
+                VRT_CUDA(cudaEventRecord(op_ev.back().second));
                 stats->kernels += 1;
             }
             VRT_CUDA(cudaGetLastError());
             VRT_TRY(sweep_run(s->g, nb, dirs.data(), s->S.p + l0, s->nlam, lc, 0, stats));
-            if (s->is_line) {
-                float ms = 0;
-                VRT_CUDA(cudaEventElapsedTime(&ms, e0, e1));
-                opacity_ms += ms;
-            }
             k_J_reduce<<<nblocks(n * lc, 256), 256>>>(n, lc, jd, s->J.p + l0, s->nlam, d0 == 0);
             stats->kernels += 1;
             VRT_CUDA(cudaGetLastError());
         }
     }
     VRT_CUDA(cudaDeviceSynchronize());
+    VRT_TRY(sweep_collect(s->g, stats));
+    for (auto& pr : op_ev) {
+        float ms = 0;
+        VRT_CUDA(cudaEventElapsedTime(&ms, pr.first, pr.second));
+        opacity_ms += ms;
+    }
+    if (s->nd == 0) VRT_CUDA(cudaMemset(s->J.p, 0, sizeof(double) * (size_t)n * s->nlam));   // no direction: J = 0, whatever J held
     if (s->dir_sharded && s->allreduce) {
         // J = sum over the direction shards (lambda_iteration.jl:102,107 add the directions one after the other)
-        if (s->nd == 0) VRT_CUDA(cudaMemset(s->J.p, 0, sizeof(double) * (size_t)n * s->nlam));
         int rc = scatter ? s->allreduce(s->J.p, s->n_pad * s->nlam, 3, s->allreduce_user)
                          : s->allreduce(s->J.p, n * s->nlam, 2, s->allreduce_user);
         if (rc != 0) {
@@ -824,8 +842,6 @@ static int mean_intensity_internal(vrt_solver* s, SweepStats* stats, double* t_o
             return VRT_E_STATE;
         }
     }
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
     if (t_opacity_ms) *t_opacity_ms = opacity_ms;
     if (t_sweep_ms) *t_sweep_ms = stats->sweep_ms;
     return VRT_OK;
@@ -994,6 +1010,7 @@ int vrt_formal_solve(vrt_grid* g, const double k[3], int32_t down, double p, int
     VRT_TRY(download_rows(g, I_main.p, I_out, nlam, stage));
     stats.kernels += 1;
     VRT_CUDA(cudaDeviceSynchronize());
+    VRT_TRY(sweep_collect(g, &stats));
     g_last_stats = stats;
     return VRT_OK;
 }
@@ -1279,7 +1296,7 @@ int vrt_lambda_iterate(vrt_solver* s, double eps, int32_t maxiter, vrt_iter_cb c
         info.diff = diff;
         VRT_TRY(mean_intensity_internal(s, &stats, &info.t_opacity_ms, &info.t_sweep_ms, cshard));
         cudaEvent_t e[4];
-        for (auto& ev : e) VRT_CUDA(cudaEventCreate(&ev));
+        for (auto& ev : e) VRT_TRY(s->event(&ev));   // pooled: mean_intensity_internal reset the pool for this iteration
         VRT_CUDA(cudaMemset(s->diff_bits.p, 0, sizeof(unsigned long long)));
         VRT_CUDA(cudaMemset(s->diff_nan.p, 0, sizeof(int)));
         VRT_CUDA(cudaEventRecord(e[0]));
@@ -1322,7 +1339,6 @@ int vrt_lambda_iterate(vrt_solver* s, double eps, int32_t maxiter, vrt_iter_cb c
             VRT_CUDA(cudaEventElapsedTime(&ms, e[2], e[3]));
             info.t_stateq_ms = ms;
         }
-        for (auto& ev : e) cudaEventDestroy(ev);
         VRT_TRY(read_diff(s, &diff));
         i++;
         info.iteration = i;
@@ -1334,7 +1350,7 @@ int vrt_lambda_iterate(vrt_solver* s, double eps, int32_t maxiter, vrt_iter_cb c
     g_last_stats = total;
     if (out) {
         out->iterations = i;
-        out->converged = !(diff > eps);
+        out->converged = (diff == diff) && !(diff > eps);   // NaN stops the loop like the reference's `while diff > eps`, but is not convergence
         out->diff = diff;
         out->seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_begin).count();
     }

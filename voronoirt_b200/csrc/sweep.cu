@@ -12,7 +12,9 @@
 //     I_c  = 0 + w_1 (e_1 I_u1 + a_1 S_u1 + b_1 S_c) + w_2 (e_2 I_u2 + a_2 S_u2 + b_2 S_c)
 // Roofline: HBM-bound; algorithmic bytes per (cell,direction,wavelength) update are given in DESIGN.md.
 #include <stdlib.h>
+#include <string.h>
 #include <algorithm>
+#include <mutex>
 #include "vrt_internal.h"
 
 namespace vrt {
@@ -28,8 +30,12 @@ struct DirDev {
     int32_t pad;
 };
 
+// the programs of the directions in flight, passed by value (kernel parameter space: no allocation, no copy per launch)
+struct DirTable {
+    DirDev d[MAX_DIRS];
+};
+
 struct SweepParams {
-    const DirDev* dirs;      // [nd] in global memory
     const double* S;         // [n][ldS], first wavelength of the chunk
     int64_t ldS;             // row stride of S
     int nd;
@@ -142,8 +148,8 @@ __device__ __forceinline__ void do_item(const VisitRegs& v, const DirDev* __rest
 // upwind intensities.  Chunks are claimed in a fixed global topological order (warp w owns chunks w, w+W, ...),
 // every warp of the cooperative launch is resident, so by induction on the chunk index no wait can deadlock.
 // Polling uses relaxed loads (an acquire load costs an L1 invalidate per poll); `acquire` adds the one acquire that
-// orders the subsequent generic-proxy reads of the intensities.  The TMA producer passes acquire=false: its reads go
-// through the async proxy (L2) and are ordered by fence.proxy.async instead.
+// orders the subsequent generic-proxy reads of the intensities.  The TMA producer polls with wait_flags2, which ends with
+// an acquire fence, and then crosses to the async proxy with fence.proxy.async before its bulk copies.
 __device__ __forceinline__ void wait_flag(const int32_t* f, int32_t epoch, bool acquire) {
     int v;
     for (;;) {
@@ -154,7 +160,7 @@ __device__ __forceinline__ void wait_flag(const int32_t* f, int32_t epoch, bool 
     if (acquire) asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
 }
 // both producer flags of a visit, polled together (one L2 round trip when they are already set)
-__device__ __forceinline__ void wait_flags2(const int32_t* flags, uint32_t d1, uint32_t d2, int32_t epoch) {
+__device__ __forceinline__ void wait_flags2(const int32_t* flags, uint32_t d1, uint32_t d2, int32_t epoch, bool acquire) {
     const int32_t* f1 = flags + (d1 == DEP_NONE ? 0 : d1);
     const int32_t* f2 = flags + (d2 == DEP_NONE ? 0 : d2);
     for (;;) {
@@ -164,6 +170,9 @@ __device__ __forceinline__ void wait_flags2(const int32_t* flags, uint32_t d1, u
         if ((d1 == DEP_NONE || v1 == epoch) && (d2 == DEP_NONE || v2 == epoch)) break;
         __nanosleep(100);
     }
+    // the relaxed polls alone order nothing: this fence makes them an acquire (it pairs with the consumers'
+    // fence.acq_rel + relaxed flag store), so the producers' result rows are visible before anything issued after it
+    if (acquire && (d1 != DEP_NONE || d2 != DEP_NONE)) asm volatile("fence.acq_rel.gpu;" ::: "memory");
 }
 // lane 0 publishes the chunk after __syncwarp(): the release is cumulative over the other lanes' stores, which are
 // ordered before it by the warp barrier (PTX memory model: causality order through bar.warp.sync)
@@ -183,7 +192,7 @@ constexpr int SWEEP_BLOCK = 256;
 #endif
 
 template <bool SINGLE>
-__global__ void __launch_bounds__(SWEEP_BLOCK, SWEEP_MIN_BLOCKS) k_sweep(const SweepParams P) {
+__global__ void __launch_bounds__(SWEEP_BLOCK, SWEEP_MIN_BLOCKS) k_sweep(const SweepParams P, const __grid_constant__ DirTable DT) {
     const int lane = threadIdx.x & 31;
     const long long nwarps = (long long)((gridDim.x * (unsigned)blockDim.x) >> 5);
     long long gnext = (long long)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);  // next global chunk of this warp
@@ -198,7 +207,7 @@ __global__ void __launch_bounds__(SWEEP_BLOCK, SWEEP_MIN_BLOCKS) k_sweep(const S
     const int G = P.T * P.nd;
     for (int g = 0; g < G; g++) {
         const int d = g % P.nd, t = g / P.nd;
-        const DirDev* __restrict__ D = P.dirs + d;
+        const DirDev* __restrict__ D = DT.d + d;
         if (t >= D->nsteps) continue;
         const int beg = __ldg(D->step_off + t);
         const int total = (__ldg(D->step_off + t + 1) - beg) / cv;
@@ -293,7 +302,7 @@ constexpr int TMA_MAX_STAGES = 32;
 
 // TMA_NP producer warps (independent issue chains) + TMA_NC consumer warps per CTA
 template <int TMA_NP, int TMA_NC>
-__global__ void __launch_bounds__(32 * (TMA_NP + TMA_NC), 3) k_sweep_tma(const SweepParams P, int ns, int rowb) {
+__global__ void __launch_bounds__(32 * (TMA_NP + TMA_NC), 3) k_sweep_tma(const SweepParams P, const __grid_constant__ DirTable DT, int ns, int rowb) {
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t* full = reinterpret_cast<uint64_t*>(smem);
     // stage hand-back: consumed[s] counts the rounds of stage s that have been drained.  A counter (not an mbarrier
@@ -308,7 +317,7 @@ __global__ void __launch_bounds__(32 * (TMA_NP + TMA_NC), 3) k_sweep_tma(const S
     const int nlam = P.nlam;
     const int32_t epoch = P.epoch;
     for (int i = threadIdx.x; i < P.nd * (int)(sizeof(DirDev) / 8); i += blockDim.x)
-        reinterpret_cast<unsigned long long*>(sdirs)[i] = reinterpret_cast<const unsigned long long*>(P.dirs)[i];
+        reinterpret_cast<unsigned long long*>(sdirs)[i] = reinterpret_cast<const unsigned long long*>(DT.d)[i];
     if (threadIdx.x == 0) {
         for (int s = 0; s < ns; s++) {
             mbar_init(full + s, 1);
@@ -352,8 +361,8 @@ __global__ void __launch_bounds__(32 * (TMA_NP + TMA_NC), 3) k_sweep_tma(const S
                     const unsigned my = it + (unsigned)lane;
                     const int stage = (int)(my % (unsigned)ns);
                     const uint32_t round = my / (unsigned)ns;
-                    wait_flags2(D->flags, v.b.z, v.b.w, epoch);
-                    asm volatile("fence.proxy.async;" ::: "memory");   // the flags were acquired through the generic proxy
+                    wait_flags2(D->flags, v.b.z, v.b.w, epoch, P.experiment != 4);   // ends with an acquire fence (generic proxy; experiment 4 times its cost)
+                    asm volatile("fence.proxy.async;" ::: "memory");   // ... which the bulk copies (async proxy) are ordered after
                     // rows of the stage: 0 α_c, 1 S_c, 2 α_u1, 3 S_u1, 4 I_u1, 5 α_u2, 6 S_u2, 7 I_u2
                     const double* src[8];
                     const double* alpha = D->alpha;
@@ -389,6 +398,10 @@ __global__ void __launch_bounds__(32 * (TMA_NP + TMA_NC), 3) k_sweep_tma(const S
                     h.pad = 0;
                     // take the stage as late as possible: its lifetime bounds the throughput of the ring
                     while (consumed[stage] != round) __nanosleep(100);
+                    // the consumer's generic-proxy reads of this stage happen before its hand-back (fence + store below);
+                    // order our async-proxy overwrite after having observed it
+                    __threadfence_block();
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     hdr[stage] = h;
                     mbar_arrive_expect_tx(full + stage, tot);
 #pragma unroll
@@ -421,6 +434,7 @@ __global__ void __launch_bounds__(32 * (TMA_NP + TMA_NC), 3) k_sweep_tma(const S
             const int stage = (int)(it % (unsigned)ns);
             if (lane == 0) {
                 while (consumed[stage] != it / (unsigned)ns) __nanosleep(32);
+                __threadfence_block();
                 hdr[stage].valid = 0;
                 hdr[stage].seq = it;
                 mbar_arrive(full + stage);
@@ -485,7 +499,10 @@ __global__ void __launch_bounds__(32 * (TMA_NP + TMA_NC), 3) k_sweep_tma(const S
                 h.dst[l] = I;
             }
             __syncwarp();   // every lane has read its part of the stage and issued its stores
-            if (lane == 0) consumed[stage] = it / (unsigned)ns + 1u;
+            if (lane == 0) {
+                __threadfence_block();   // release: the warp's reads of the stage are ordered before the hand-back
+                consumed[stage] = it / (unsigned)ns + 1u;
+            }
             pend[np++] = h.flag;
             long long k2 = 0;
             if (P.experiment == 2) k2 = clock64();
@@ -505,6 +522,36 @@ __global__ void __launch_bounds__(32 * (TMA_NP + TMA_NC), 3) k_sweep_tma(const S
     }
 }
 
+// events of the launches since the last sweep_collect(): (start, stop) pairs from a pool owned by the grid
+struct SweepTimers {
+    std::vector<cudaEvent_t> pool;   // 2 per launch
+    size_t used = 0;
+    ~SweepTimers() {
+        for (auto e : pool) cudaEventDestroy(e);
+    }
+};
+static SweepTimers* timers_of(vrt_grid* g) {
+    if (!g->sweep_timers) g->sweep_timers = new SweepTimers();
+    return static_cast<SweepTimers*>(g->sweep_timers);
+}
+void sweep_timers_free(void* p) { delete static_cast<SweepTimers*>(p); }
+
+// Adds the kernel time of the launches recorded since the last call to stats->sweep_ms.  The stream must have been
+// synchronised by the caller (no launch of this grid in flight).
+int sweep_collect(vrt_grid* g, SweepStats* stats) {
+    std::lock_guard<std::recursive_mutex> lock(g->mu);
+    SweepTimers* T = timers_of(g);
+    for (size_t i = 0; i + 1 < T->used; i += 2) {
+        float ms = 0;
+        VRT_CUDA(cudaEventElapsedTime(&ms, T->pool[i], T->pool[i + 1]));
+        if (stats) stats->sweep_ms += ms;
+    }
+    T->used = 0;
+    return VRT_OK;
+}
+
+// Launches the merged sweep program asynchronously on `st` (no host synchronisation, no allocation in steady state).
+// The kernel time is accounted for by sweep_collect() after the caller has synchronised.
 int sweep_run(vrt_grid* g, int nd, const SweepDir* dirs, const double* S, int64_t ldS, int64_t nlam, cudaStream_t st, SweepStats* stats) {
     if (nd <= 0) return VRT_OK;
     if (nd > MAX_DIRS) {
@@ -523,6 +570,14 @@ int sweep_run(vrt_grid* g, int nd, const SweepDir* dirs, const double* S, int64_
     }
     if (T == 0) return VRT_OK;
 
+    // the flag pool and the epoch belong to the grid, which solvers and host threads may share: one launch at a time
+    // carves its flags and takes its epoch (launches of one grid are also serialised on the device: the flags of a
+    // launch must not be reused before it has finished, so all launches of a grid go through one stream order)
+    std::lock_guard<std::recursive_mutex> lock(g->mu);
+    if (g->sweep_stream_set && g->sweep_stream != st) VRT_CUDA(cudaStreamSynchronize(g->sweep_stream));
+    g->sweep_stream = st;
+    g->sweep_stream_set = true;
+
     // ready-flags: one int per chunk, carved from a pool that is never cleared (flag == epoch <=> done now)
     const int cv = dirs[0].sch->cv;
     size_t nflags = 0;
@@ -534,30 +589,29 @@ int sweep_run(vrt_grid* g, int nd, const SweepDir* dirs, const double* S, int64_
         nflags += (size_t)dirs[d].sch->n_chunks;
     }
     if (g->flag_pool.n < nflags || g->epoch >= INT32_MAX - 1) {
+        VRT_CUDA(cudaStreamSynchronize(st));   // an earlier launch may still be using the old pool
         VRT_TRY(g->flag_pool.alloc(nflags));
         VRT_CUDA(cudaMemsetAsync(g->flag_pool.p, 0, sizeof(int32_t) * g->flag_pool.n, st));
         g->epoch = 0;
     }
     const int32_t epoch = ++g->epoch;
-    std::vector<DirDev> hd(nd);
+    DirTable DT;
+    memset(&DT, 0, sizeof(DT));
     size_t fo = 0;
     for (int d = 0; d < nd; d++) {
-        hd[d].flags = g->flag_pool.p + fo;
+        DirDev& h = DT.d[d];
+        h.flags = g->flag_pool.p + fo;
         fo += (size_t)dirs[d].sch->n_chunks;
-        hd[d].step_off = dirs[d].sch->step_off_dev.p;
-        hd[d].nsteps = (int32_t)dirs[d].sch->step_off.size() - 1;
-        hd[d].pad = 0;
-        hd[d].visits = dirs[d].sch->visits.p;
-        hd[d].alpha = dirs[d].alpha;
-        hd[d].I_main = dirs[d].I_main;
-        for (int s = 0; s < MAX_SWEEPS; s++) hd[d].scratch[s] = dirs[d].scratch[s];
+        h.step_off = dirs[d].sch->step_off_dev.p;
+        h.nsteps = (int32_t)dirs[d].sch->step_off.size() - 1;
+        h.pad = 0;
+        h.visits = dirs[d].sch->visits.p;
+        h.alpha = dirs[d].alpha;
+        h.I_main = dirs[d].I_main;
+        for (int s = 0; s < MAX_SWEEPS; s++) h.scratch[s] = dirs[d].scratch[s];
     }
-    DevBuf<DirDev> d_dirs;
-    VRT_TRY(d_dirs.alloc(nd));
-    VRT_CUDA(cudaMemcpyAsync(d_dirs.p, hd.data(), sizeof(DirDev) * nd, cudaMemcpyHostToDevice, st));
 
     SweepParams P;
-    P.dirs = d_dirs.p;
     P.S = S;
     P.ldS = ldS;
     P.nd = nd;
@@ -567,18 +621,22 @@ int sweep_run(vrt_grid* g, int nd, const SweepDir* dirs, const double* S, int64_
     P.epoch = epoch;
     P.run_len = getenv("VRT_RUN_LEN") ? std::max(1, std::min(32, atoi(getenv("VRT_RUN_LEN")))) : 32;
     P.experiment = getenv("VRT_EXPERIMENT") ? atoi(getenv("VRT_EXPERIMENT")) : 0;
+    P.prof = nullptr;
     DevBuf<unsigned long long> d_prof;
-    VRT_TRY(d_prof.alloc(16));
-    VRT_CUDA(cudaMemsetAsync(d_prof.p, 0, 16 * sizeof(unsigned long long), st));
-    P.prof = d_prof.p;
+    if (P.experiment == 2) {
+        VRT_TRY(d_prof.alloc(16));
+        VRT_CUDA(cudaMemsetAsync(d_prof.p, 0, 16 * sizeof(unsigned long long), st));
+        P.prof = d_prof.p;
+    }
 
-    int dev = 0, sms = 0, per_sm = 0;
+    int dev = 0, sms = 0, per_sm = 0, smem_max = 0;
     VRT_CUDA(cudaGetDevice(&dev));
     VRT_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    VRT_CUDA(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
     const char* env_tma = getenv("VRT_TMA");
-    const bool use_tma = P.cv == 1 && nlam >= 16 && !(env_tma && atoi(env_tma) == 0);
-    const void* fn;
-    int block, ns = 0, rowb = 0;
+    bool use_tma = P.cv == 1 && nlam >= 16 && !(env_tma && atoi(env_tma) == 0);
+    const void* fn = nullptr;
+    int block = 0, ns = 0, rowb = 0;
     size_t shmem = 0;
     if (use_tma) {
         const char* env_cfg = getenv("VRT_TMA_CFG");
@@ -600,10 +658,14 @@ int sweep_run(vrt_grid* g, int nd, const SweepDir* dirs, const double* S, int64_
         if (env_ns && atoi(env_ns) > 0) ns = atoi(env_ns);
         ns = std::max(2, std::min(ns, TMA_MAX_STAGES));
         shmem = fixed + (size_t)ns * 8 * rowb;
-        VRT_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
-    } else {
+        // very wide rows (vrt_formal_solve with hundreds of wavelengths): two stages no longer fit one CTA -> register path
+        if (shmem > (size_t)smem_max) use_tma = false;
+        else VRT_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
+    }
+    if (!use_tma) {
         fn = P.cv == 1 ? (const void*)k_sweep<true> : (const void*)k_sweep<false>;
         block = SWEEP_BLOCK;
+        shmem = 0;
     }
     VRT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, block, shmem));
     if (per_sm < 1) {
@@ -611,37 +673,34 @@ int sweep_run(vrt_grid* g, int nd, const SweepDir* dirs, const double* S, int64_
         return VRT_E_CUDA;
     }
     int grid = sms * per_sm;
-    cudaEvent_t e0, e1;
-    VRT_CUDA(cudaEventCreate(&e0));
-    VRT_CUDA(cudaEventCreate(&e1));
-    VRT_CUDA(cudaEventRecord(e0, st));
-    void* args[] = {(void*)&P, (void*)&ns, (void*)&rowb};
-    cudaError_t le = cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(block), args, shmem, st);
-    if (le != cudaSuccess) {
-        cudaEventDestroy(e0);
-        cudaEventDestroy(e1);
-        return cuda_fail(le, "cudaLaunchCooperativeKernel(k_sweep)", __FILE__, __LINE__);
+    SweepTimers* TM = timers_of(g);
+    if (TM->used + 2 > TM->pool.size()) {
+        for (int i = 0; i < 2; i++) {
+            cudaEvent_t e;
+            VRT_CUDA(cudaEventCreate(&e));
+            TM->pool.push_back(e);
+        }
     }
+    cudaEvent_t e0 = TM->pool[TM->used], e1 = TM->pool[TM->used + 1];
+    VRT_CUDA(cudaEventRecord(e0, st));
+    void* args[] = {(void*)&P, (void*)&DT, (void*)&ns, (void*)&rowb};
+    cudaError_t le = cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(block), args, shmem, st);
+    if (le != cudaSuccess) return cuda_fail(le, "cudaLaunchCooperativeKernel(k_sweep)", __FILE__, __LINE__);
     VRT_CUDA(cudaEventRecord(e1, st));
-    VRT_CUDA(cudaEventSynchronize(e1));  // also keeps the program tables alive until the kernel is done
-    float ms = 0;
-    VRT_CUDA(cudaEventElapsedTime(&ms, e0, e1));
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
-    VRT_CUDA(cudaGetLastError());
+    TM->used += 2;
     if (P.experiment == 2) {
+        VRT_CUDA(cudaStreamSynchronize(st));
         unsigned long long h[16];
         VRT_CUDA(cudaMemcpy(h, d_prof.p, sizeof(h), cudaMemcpyDeviceToHost));
-        fprintf(stderr, "[sweep prof] %.2f ms | producer lane: flags %.0f cyc, stage %.0f cyc per visit (%llu visits) | run %.0f cyc (%llu runs) | "
+        fprintf(stderr, "[sweep prof] producer lane: flags %.0f cyc, stage %.0f cyc per visit (%llu visits) | run %.0f cyc (%llu runs) | "
                         "consumer per visit: wait %.0f, compute %.0f, release %.0f cyc (%llu)\n",
-                ms, (double)h[0] / (h[2] + 1e-9), (double)h[1] / (h[2] + 1e-9), h[2], (double)h[3] / (h[4] + 1e-9), h[4],
+                (double)h[0] / (h[2] + 1e-9), (double)h[1] / (h[2] + 1e-9), h[2], (double)h[3] / (h[4] + 1e-9), h[4],
                 (double)h[5] / (h[8] + 1e-9), (double)h[6] / (h[8] + 1e-9), (double)h[7] / (h[8] + 1e-9), h[8]);
     }
     if (stats) {
         stats->kernels += 1;
         stats->visits += visits;
         stats->steps += (double)T * nd;
-        stats->sweep_ms += ms;
     }
     return VRT_OK;
 }

@@ -9,6 +9,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <mutex>
 #include <string>
 #include <vector>
 #include "../../include/vrt.h"
@@ -97,8 +98,18 @@ struct Stencil {
     DevBuf<double> r;       // 2*n
 };
 
+// order of the visits of a wide-row program (schedule.cu, rule 5)
+struct OrderCfg {
+    int bx = 1, by = 1;     // column blocks in x and y
+    int slab = 0;           // levels per slab (0: one slab)
+    int step_min = 2048;    // visits per step of the blocked program (steps only interleave the directions in flight)
+    bool blocked() const { return bx * by > 1 || slab > 0; }
+    bool operator==(const OrderCfg& o) const { return bx == o.bx && by == o.by && slab == o.slab && step_min == o.step_min; }
+};
+
 struct DirSchedule {
     double k[3];
+    OrderCfg order;
     int down = 0;
     int n_sweeps = 3;
     int prune = 1;
@@ -113,7 +124,8 @@ struct DirSchedule {
     // (layer, sweep) -> number of sub-levels; index (layer-2)*n_sweeps + (sweep-1)
     std::vector<int32_t> nsub;
     int64_t scr_rows[MAX_SWEEPS] = {0};  // rows needed in scratch buffer s (sweep s+1 non-final writers)
-    // introspection (internal order)
+    int64_t n_pushed = 0;           // blocked order: visits whose key was pushed behind a producer of a later block
+    // introspection (internal order); released after the build unless asked for (vrt_grid_get_schedule)
     DevBuf<int32_t> cls;       // 2*n
     DevBuf<int32_t> sublevel;  // n (sweep 1)
     DevBuf<int32_t> stab;      // n
@@ -144,6 +156,13 @@ struct vrt_grid {
     // ready-flags of the dataflow sweep: flag == epoch <=> chunk done in the current launch (no memset per launch)
     vrt::DevBuf<int32_t> flag_pool;
     int32_t epoch = 0;
+    // a vrt_grid may be shared by several solvers / host threads: the schedule cache, the flag pool and the epoch are
+    // guarded by this mutex (held from the flag carve-out to the end of the sweep launch)
+    std::recursive_mutex mu;
+    // stream order all sweep launches of this grid go through, and the event pool that times them (sweep.cu)
+    cudaStream_t sweep_stream = 0;
+    bool sweep_stream_set = false;
+    void* sweep_timers = nullptr;
     // regular Cartesian grid (vrt_regular_grid_create): cells in the Julia (nz, nx, ny) order, identity permutation,
     // no layers / stencils / schedules; the formal solver is regular.cu's plane walk
     bool regular = false;
@@ -159,10 +178,14 @@ int grid_build(vrt_grid* g, const double* positions, const int64_t* nbr, int64_t
 int grid_stencil(vrt_grid* g, const double k[3], double p, Stencil* st);
 
 // schedule.cu
-int schedule_build(vrt_grid* g, const double k[3], int down, int n_sweeps, double p, int prune, int cv, DirSchedule** out);
+OrderCfg order_config(int64_t n, int cv);   // from the environment (VRT_BLOCKS, VRT_SLAB, VRT_STEP_MIN) or the defaults for n sites
+int schedule_build(vrt_grid* g, const double k[3], int down, int n_sweeps, double p, int prune, int cv, const OrderCfg& oc,
+                   bool keep_introspection, DirSchedule** out);
+// cached per grid (no introspection arrays); serialised by the grid's mutex
 DirSchedule* schedule_get(vrt_grid* g, const double k[3], int down, int n_sweeps, double p, int prune, int cv, int* rc);
-// visits per chunk for rows of nlam wavelengths
-inline int chunk_visits(int64_t nlam) { return nlam >= 16 ? 1 : (nlam >= 24 ? 2 : (nlam >= 12 ? 4 : (nlam >= 6 ? 8 : (nlam >= 3 ? 16 : 32)))); }
+void schedule_cache_clear(vrt_grid* g);
+// visits per chunk for rows of nlam wavelengths (wide rows: one visit per chunk, TMA pipeline)
+inline int chunk_visits(int64_t nlam) { return nlam >= 16 ? 1 : (nlam >= 12 ? 4 : (nlam >= 6 ? 8 : (nlam >= 3 ? 16 : 32))); }
 
 // sweep.cu
 struct SweepDir {
@@ -175,7 +198,10 @@ struct SweepStats {
     double kernels = 0, visits = 0, steps = 0, sweep_ms = 0;
 };
 // runs the merged sweep program of `nd` directions over nlam wavelengths; S is [n][ldS] (pointer at the chunk's first λ)
+// asynchronous launch on `st`; sweep_collect() adds the kernel times of the launches since the last call once the caller has synchronised
 int sweep_run(vrt_grid* g, int nd, const SweepDir* dirs, const double* S, int64_t ldS, int64_t nlam, cudaStream_t st, SweepStats* stats);
+int sweep_collect(vrt_grid* g, SweepStats* stats);
+void sweep_timers_free(void* p);
 int sweep_scratch_rows(const DirSchedule* sch, int s);
 
 // misc kernels (physics.cu)
