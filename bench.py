@@ -31,18 +31,27 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WORKLOADS = {
-    # name: (base sites tessellated by voro++, tiles in x, tiles in y, quadrature, nλ_bb, nλ_bf)
+    # name: (base sites, tiles in x, tiles in y, quadrature, nλ_bb, nλ_bf)
+    # *_native: sites sampled from the synthetic atmosphere cube and tessellated ON THE GPU (vrt_rejection_sampling,
+    # vrt_voronoi_neighbours, vrt_trilinear: the reference's set-up pipeline without voro++), no tiling.
+    "nlte_16m_native": (16000000, 1, 1, "ul9n20", 50, 20),   # DEFAULT: BASELINE configs[4] / the north-star target
+    "nlte_4m_native": (4000000, 1, 1, "ul9n20", 50, 20),
+    "nlte_1m_native": (1000000, 1, 1, "ul7n12", 50, 20),     # BASELINE configs[2] (λ-sharded at N > 1 with --shard lambda)
+    # voro++ tessellation of `base` sites, tiled periodically in x and y (round-1 workloads, kept for comparison)
     "small": (20000, 1, 1, "ul7n12", 50, 20),
     "nlte_1m": (250000, 2, 2, "ul7n12", 50, 20),
-    "nlte_1m_direct": (1000000, 1, 1, "ul7n12", 50, 20),   # 1 M sites tessellated directly (no tiling): slower set-up, same solve
+    "nlte_1m_direct": (1000000, 1, 1, "ul7n12", 50, 20),
     "nlte_4m": (250000, 4, 4, "ul9n20", 50, 20),
     "nlte_16m": (250000, 8, 8, "ul9n20", 50, 20),
-    # directly sampled sites, tessellated on the GPU by vrt_voronoi_neighbours (no voro++, no tiling)
-    "nlte_4m_native": (4000000, 1, 1, "ul9n20", 50, 20),
-    "nlte_16m_native": (16000000, 1, 1, "ul9n20", 50, 20),
+    # BASELINE configs[1]: 500 nm continuum Λ-iteration, 1 M sites, ul7n12, one wavelength
+    "continuum_1m": (1000000, 1, 1, "ul7n12", 0, 0),
+    # BASELINE configs[0]: searchlight beam test, 51^3 uniform sites, the ul7n12 directions one at a time (p = 7)
+    "searchlight": (132651, 1, 1, "ul7n12", 0, 0),
     # BASELINE configs[3]: the regular-grid comparison solver, 256 x 256 x 400 (+ ghost columns), ul7n12, 91 wavelengths (N = 1 only)
     "regular_400": (0, 1, 1, "ul7n12", 50, 20),
 }
+NATIVE = ("nlte_16m_native", "nlte_4m_native", "nlte_1m_native", "continuum_1m")
+CPU_ARM_SITES = 500000   # --impl reference on a *_native workload: sites of its voro++-tessellated sample of the same atmosphere
 
 
 def log(*a):
@@ -50,35 +59,85 @@ def log(*a):
         print("[bench]", *a, file=sys.stderr, flush=True)
 
 
-def build_problem(workload):
-    """-> dict(pos, nbr, bounds, atm, n, quadrature path).  The base tessellation is cached under .vrt_cache/."""
+def _oracle():
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle as O
+    return O
+
+
+def build_problem(workload, cpu_arm=False):
+    """-> dict(pos, nbr, bounds, atm, n, quadrature path, ...).
+    cpu_arm: the problem of `--impl reference`.  Its process must never load libvrt.so, so neighbour files are parsed by
+    the oracle, and a *_native workload (whose 16 M sites only the GPU tessellates in seconds; voro++ needs ~0.5 h) is
+    represented by CPU_ARM_SITES sites drawn from the same atmosphere cube by the same rule and tessellated by the
+    reference's own voro++ driver."""
     from voronoirt_b200 import api, synth
     base, kx, ky, qname, nbb, nbf = WORKLOADS[workload]
     cache = os.environ.get("VRT_CACHE", os.path.join(ROOT, ".vrt_cache"))
     os.makedirs(cache, exist_ok=True)
-    f = os.path.join(cache, f"base_{base}_seed2022.npz")
     rank = int(os.environ.get("RANK", "0"))
-    if workload.endswith("_native"):
+    parse = None
+    if cpu_arm:
+        O = _oracle()
+        parse = lambda fname, n: np.asfortranarray(O.read_neighbours(fname, n).T)   # noqa: E731
+    common = dict(qpath=api.quadrature_path(qname), qname=qname, nbb=nbb, nbf=nbf)
+    if workload == "searchlight":
+        # compare_searchlight.jl:10-40: n_sites = 51^3 uniform in the unit box, seed 2022
+        f = os.path.join(cache, "searchlight_132651.npz")
+        if not os.path.exists(f):
+            rng = np.random.default_rng(2022)
+            pos = np.asfortranarray(rng.random((3, base)))
+            B1 = dict(z_min=0.0, z_max=1.0, x_min=0.0, x_max=1.0, y_min=0.0, y_max=1.0)
+            if api.default_voro_exec() is not None:
+                nbr = synth.voronoi_neighbours(pos, bounds=B1, parse=parse)
+            elif not cpu_arm:
+                nbr = api.voronoi_neighbours(pos, 0.0, 1.0, 0.0, 1.0, 0.0, 1.0)
+            else:
+                raise FileNotFoundError("voro++ driver not staged (baseline/_ref/output_sites)")
+            np.savez(f + ".tmp.npz", pos=pos, nbr=nbr.astype(np.int32))
+            os.replace(f + ".tmp.npz", f)
+        d = np.load(f)
+        pos, nbr = np.asfortranarray(d["pos"]), np.asfortranarray(d["nbr"].astype(np.int64))
+        return dict(pos=pos, nbr=nbr, bounds=dict(z_min=0.0, z_max=1.0, x_min=0.0, x_max=1.0, y_min=0.0, y_max=1.0), atm=None,
+                    n=pos.shape[1], tiles=(1, 1), base=base, **common)
+    if workload in NATIVE and not cpu_arm:
         t = time.time()
-        pos = synth.sample_sites(base, seed=2022)
+        pos, atm = synth.native_sites(base, seed=2022)
         t1 = time.time()
         B = synth.BOX
         nbr = api.voronoi_neighbours(pos, B["z_min"], B["z_max"], B["x_min"], B["x_max"], B["y_min"], B["y_max"])
-        log(f"sampled {base} sites in {t1 - t:.1f}s, tessellated them on the GPU in {time.time() - t1:.2f}s (max {int(nbr[:, 0].max())} faces)")
-        atm = synth.atmosphere(pos[0], pos[1], pos[2])
-        return dict(pos=pos, nbr=nbr, bounds=dict(synth.BOX), atm=atm, n=pos.shape[1], qpath=api.quadrature_path(qname), qname=qname,
-                    nbb=nbb, nbf=nbf, tiles=(1, 1), base=base, native=True)
+        log(f"sampled and initialised {base} sites on the GPU in {t1 - t:.1f}s (cube included), tessellated them in {time.time() - t1:.2f}s "
+            f"(max {int(nbr[:, 0].max())} faces)")
+        return dict(pos=pos, nbr=nbr, bounds=dict(synth.BOX), atm=atm, n=pos.shape[1], tiles=(1, 1), base=base, native=True, **common)
+    if workload in NATIVE:   # CPU arm of a native workload
+        nref = min(base, CPU_ARM_SITES)
+        f = os.path.join(cache, f"cpu_arm_{nref}_seed2022.npz")
+        if not os.path.exists(f):
+            t = time.time()
+            pos, atm = synth.native_sites_cpu(nref, seed=2022)
+            nbr = synth.voronoi_neighbours(pos, parse=parse)
+            np.savez(f + ".tmp.npz", pos=pos, nbr=nbr.astype(np.int32), **atm)
+            os.replace(f + ".tmp.npz", f)
+            log(f"CPU arm: sampled {nref} sites (numpy) and tessellated them with voro++ in {time.time() - t:.1f}s")
+        d = np.load(f)
+        pos, nbr = np.asfortranarray(d["pos"]), np.asfortranarray(d["nbr"].astype(np.int64))
+        atm = {k: d[k] for k in synth.FIELDS}
+        return dict(pos=pos, nbr=nbr, bounds=dict(synth.BOX), atm=atm, n=pos.shape[1], tiles=(1, 1), base=base, native=True,
+                    spatial_sample=f"{nref} of {base} sites", **common)
+    f = os.path.join(cache, f"base_{base}_seed2022.npz")
     if not os.path.exists(f):
         if rank == 0:
             t = time.time()
             pos = synth.sample_sites(base, seed=2022)
             if api.default_voro_exec() is not None:
-                nbr = synth.voronoi_neighbours(pos)
+                nbr = synth.voronoi_neighbours(pos, parse=parse)
                 how = "voro++"
-            else:   # the reference's driver was not staged (oracle/_ref/output_sites): same neighbour sets from the GPU
+            elif not cpu_arm:   # the reference's driver was not staged (baseline/_ref/output_sites): same neighbour sets from the GPU
                 B = synth.BOX
                 nbr = api.voronoi_neighbours(pos, B["z_min"], B["z_max"], B["x_min"], B["x_max"], B["y_min"], B["y_max"])
                 how = "vrt_voronoi_neighbours (voro++ driver not found)"
+            else:
+                raise FileNotFoundError("voro++ driver not staged (baseline/_ref/output_sites)")
             np.savez(f + ".tmp.npz", pos=pos, nbr=nbr.astype(np.int32))
             os.replace(f + ".tmp.npz", f)
             log(f"tessellated {base} base sites with {how} in {time.time() - t:.1f}s")
@@ -93,8 +152,7 @@ def build_problem(workload):
     if kx * ky > 1:
         pos, nbr, bounds = synth.tile_grid(pos, nbr, kx, ky)
         atm = {k: np.tile(v, kx * ky) for k, v in atm.items()}
-    return dict(pos=pos, nbr=nbr, bounds=bounds, atm=atm, n=pos.shape[1], qpath=api.quadrature_path(qname), qname=qname,
-                nbb=nbb, nbf=nbf, tiles=(kx, ky), base=base)
+    return dict(pos=pos, nbr=nbr, bounds=bounds, atm=atm, n=pos.shape[1], tiles=(kx, ky), base=base, **common)
 
 
 def shard_grid(world, ndirs):
@@ -166,12 +224,13 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def cpu_reference_sample(P, line, inputs, threads, target_updates=2.0e8, hoist=0):
+def cpu_reference_sample(P, line, inputs, threads, target_updates=2.0e8, hoist=0, keep_J=False):
     """times the CPU oracle (port of the reference algorithm, threads over wavelengths like lambda_iteration.jl:91)
-    on a bounded sample: all directions x a contiguous block of wavelengths around the line centre."""
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import oracle as O
+    on a bounded sample: the first directions of the quadrature x a contiguous block of wavelengths around the line centre x
+    all sites.  The OpenMP thread count is set explicitly (torchrun exports OMP_NUM_THREADS=1)."""
+    O = _oracle()
     from voronoirt_b200 import api, atom
+    threads = O.set_num_threads(max(1, threads))
     lte, α_cont, ελ, Cr = inputs
     atm = P["atm"]
     b = P["bounds"]
@@ -182,20 +241,81 @@ def cpu_reference_sample(P, line, inputs, threads, target_updates=2.0e8, hoist=0
                           alpha_cont=α_cont, destruction=ελ, C=np.ascontiguousarray(Cr.T), lte_pops=np.ascontiguousarray(lte.T))
     w, th, ph, nq = api.read_quadrature(P["qpath"])
     nlam = len(line.λ)
-    nl_ = min(nlam, max(1, threads))
-    kd = int(min(nq, max(1, round(target_updates / (P["n"] * nl_)))))      # bounded sample: first kd directions of the table
+    nl = min(nlam, threads)
+    kd = int(min(nq, max(1, round(target_updates / (P["n"] * nl)))))      # bounded sample: first kd directions of the table
     w, th, ph, nq = w[:kd], th[:kd], ph[:kd], kd
     oq = O.make_quadrature(w, th, ph)
     S = np.ascontiguousarray(atom.B_λ(line.λ[None, :], atm["temperature"][:, None]))
     ls = line.as_struct()
-    nl = min(nlam, max(1, threads))
     l0 = max(0, line.λidx[1] // 2 - nl // 2)
+    box = {}
 
     def run():
         t = time.perf_counter()
-        O.J_lambda_voronoi(osites, ls, line.λ, sd, oq, S, lte.T, l0=l0, l1=l0 + nl, hoist=hoist)
-        return time.perf_counter() - t
-    return run, dict(nlam_sample=nl, l0=l0, ndirs=int(nq), n=P["n"], threads=O.num_threads())
+        J, _ = O.J_lambda_voronoi(osites, ls, line.λ, sd, oq, S, lte.T, l0=l0, l1=l0 + nl, hoist=hoist)
+        dt = time.perf_counter() - t
+        if keep_J:
+            box["J"] = np.ascontiguousarray(J[:, l0:l0 + nl])     # (n, nl)
+        return dt
+    return run, dict(nlam_sample=nl, l0=l0, ndirs=int(nq), n=P["n"], threads=threads, quad=(w, th, ph), S=S, box=box)
+
+
+def gpu_parity_on_sample(V, sites, P, line, inputs, info):
+    """the CUDA path on exactly the shard the CPU baseline just solved (same directions, same wavelengths, same S and
+    populations, all sites), through the C ABI with host buffers -> error measures against the oracle's J"""
+    lte, α_cont, ελ, Cr = inputs
+    Jo = info["box"].get("J")
+    if Jo is None:
+        return None
+    l0, nl = info["l0"], info["nlam_sample"]
+    solver = V.Solver(sites, info["quad"], line=line, α_cont=α_cont, ελ=ελ, C_rates=Cr, LTE_pops=lte, lam_range=(l0, l0 + nl))
+    try:
+        S = np.asfortranarray(info["S"][:, l0:l0 + nl].T)          # (nl, n)
+        Jg = solver.mean_intensity(S, lte).T                        # (n, nl)
+    finally:
+        solver.close()
+    d = np.abs(Jg - Jo)
+    scale = float(np.abs(Jo).max())
+    pos = Jo > 1e-300
+    return {"what": f"J of {info['ndirs']} direction(s) x {nl} wavelengths x {info['n']} sites: CUDA path (vrt_mean_intensity, host buffers) against the CPU oracle, same inputs",
+            "max_rel_err": float(d.max() / scale), "max_pointwise_rel_err": float((d[pos] / Jo[pos]).max()) if pos.any() else 0.0,
+            "tolerance": 1e-9, "ok": bool(d.max() / scale <= 1e-9), "sites": int(info["n"]), "n_values": int(Jo.size)}
+
+
+METRIC = "cell*angle*freq updates/s per formal solution (NLTE Lambda-iteration)"
+
+
+def reference_arm(args, W, K):
+    """--impl reference: the CPU port of the reference's J_λ_voronoi on the host cores, bounded sample per step.  This process
+    never loads libvrt.so (neighbour files are parsed by the oracle)."""
+    from voronoirt_b200 import synth
+    P = build_problem(args.workload, cpu_arm=True)
+    atm = P["atm"]
+    line, lte, α_cont, ελ, Cr = synth.line_inputs(atm["temperature"], atm["electron_density"], atm["hydrogen_density"], P["nbb"], P["nbf"])
+    threads = os.cpu_count() or 1
+    # size the sample for roughly 15 s per step: calibrate on one direction, then take as many directions as fit
+    run1, info1 = cpu_reference_sample(P, line, (lte, α_cont, ελ, Cr), threads, target_updates=1.0)
+    t1 = run1()
+    per_update = t1 / (info1["n"] * info1["ndirs"] * info1["nlam_sample"])
+    target = max(1.0, float(os.environ.get("VRT_CPU_STEP_SECONDS", "15")) / per_update)
+    run, info = cpu_reference_sample(P, line, (lte, α_cont, ελ, Cr), threads, target_updates=target)
+    for _ in range(min(W, 1)):
+        run()
+    ts = [run() for _ in range(K)]
+    t = float(np.mean(ts))
+    updates = info["n"] * info["ndirs"] * info["nlam_sample"]
+    val = updates / t
+    sample = (f"{info['nlam_sample']} of {len(line.λ)} wavelengths (index {info['l0']}..) x the first {info['ndirs']} of the quadrature's directions x {info['n']} sites"
+              + (f" (spatial sample: {P['spatial_sample']} of the workload, drawn from the same atmosphere by the same rule and tessellated by the reference's voro++ driver)" if P.get("spatial_sample") else "")
+              + ", stencil recomputed at every visit like irregular_ray_tracing.jl:50; C/OpenMP port of the Julia reference (Julia not installed), -O3 -march=native")
+    out = {"impl": "reference", "metric": METRIC, "value": val,
+           "unit": "updates/s", "n_gpus": args.gpus, "steps": K, "warmup": min(W, 1), "ms_per_step": 1e3 * t, "higher_is_better": True,
+           "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": {"workload": workload_name(args.workload, P, len(line.λ)), "sites": WORKLOADS[args.workload][0] * WORKLOADS[args.workload][1] * WORKLOADS[args.workload][2],
+                      "quadrature": P["qname"], "n_lambda": len(line.λ)},
+           "cpu_baseline": {"value": val, "unit": "updates/s", "cores": info["threads"], "kind": "port", "sample": sample},
+           "e2e": {"value": val, "unit": "updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    return _line(out)
 
 
 def main():
@@ -203,8 +323,10 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--workload", default=os.environ.get("VRT_WORKLOAD", "nlte_16m"), choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default=os.environ.get("VRT_WORKLOAD", "nlte_16m_native"), choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--shard", default=os.environ.get("VRT_SHARD", "auto"), choices=["auto", "lambda"],
+                    help="N > 1: auto = direction shards first (then wavelengths); lambda = wavelength shards only (BASELINE configs[2])")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -216,31 +338,12 @@ def main():
 
     if args.workload.startswith("regular"):
         return main_regular(args, W, K)
+    if args.workload == "searchlight":
+        return main_searchlight(args, W, K)
+    if args.workload.startswith("continuum"):
+        return main_continuum(args, W, K)
     if args.impl == "reference":
-        if rank != 0:
-            return 0
-        from voronoirt_b200 import synth
-        P = build_problem(args.workload)
-        atm = P["atm"]
-        line, lte, α_cont, ελ, Cr = synth.line_inputs(atm["temperature"], atm["electron_density"], atm["hydrogen_density"], P["nbb"], P["nbf"])
-        threads = os.cpu_count() or 1
-        run, info = cpu_reference_sample(P, line, (lte, α_cont, ελ, Cr), threads)
-        for _ in range(min(W, 1)):
-            run()
-        ts = [run() for _ in range(K)]
-        t = float(np.mean(ts))
-        updates = info["n"] * info["ndirs"] * info["nlam_sample"]
-        val = updates / t
-        sample = (f"{info['nlam_sample']} of {len(line.λ)} wavelengths (index {info['l0']}..) x the first {info['ndirs']} of the quadrature's directions x {info['n']} sites, "
-                  "stencil recomputed at every visit like irregular_ray_tracing.jl:50; C/OpenMP port of the Julia reference (Julia not installed)")
-        out = {"impl": "reference", "metric": "cell*angle*freq updates/s per formal solution (NLTE Lambda-iteration)", "value": val,
-               "unit": "updates/s", "n_gpus": args.gpus, "steps": K, "warmup": min(W, 1), "ms_per_step": 1e3 * t, "higher_is_better": True,
-               "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-               "config": {"workload": workload_name(args.workload, P, len(line.λ)), "sites": P["n"], "quadrature": P["qname"], "n_lambda": len(line.λ)},
-               "cpu_baseline": {"value": val, "unit": "updates/s", "cores": info["threads"], "kind": "port", "sample": sample},
-               "e2e": {"value": val, "unit": "updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(out))
-        return 0
+        return reference_arm(args, W, K) if rank == 0 else 0
 
     import torch
     import voronoirt_b200 as V
@@ -248,9 +351,16 @@ def main():
     torch.cuda.set_device(local_rank)
     _lib.check(_lib.lib().vrt_set_device(local_rank))
     dist = None
+    nccl_log = None
     if world > 1:
         import torch.distributed as dist
-        os.environ["NCCL_DEBUG"] = "WARN"   # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
+        # NCCL's INFO log (rings / NVLS, which tells whether the switch reduces) goes to a file per rank, not to stdout:
+        # rank 0 prints exactly one JSON line
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        nccl_log = os.path.join(ROOT, "gpurun_out", f"nccl_n{world}_rank%r.log".replace("%r", str(rank)))
+        os.environ.setdefault("NCCL_DEBUG", "INFO")
+        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT,GRAPH,ENV")
+        os.environ.setdefault("NCCL_DEBUG_FILE", nccl_log)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     t_setup = time.time()
@@ -261,60 +371,24 @@ def main():
     w, th, ph, nq = V.read_quadrature(P["qpath"])
     # multi-GPU decomposition: D direction shards x G wavelength shards (D*G = world).  Directions first: the sweep's cost
     # is per (cell, direction) visit, so fewer directions per GPU scales it, narrower wavelength rows barely do.
-    D, G = shard_grid(world, int(nq))
+    D, G = (1, world) if args.shard == "lambda" else shard_grid(world, int(nq))
     di, gi = rank % D, rank // D
     lo, hi = shard_range(nlam, G, gi)
-    # directions are dealt round-robin (rank di takes di, di+D, ...): neighbouring lines of the quadrature files are up/down
-    # pairs of similar inclination, so every rank gets a similar mix of cheap (steep) and expensive (grazing) directions
-    mine = list(range(di, int(nq), D))
-    my_quad = (w[mine], th[mine], ph[mine]) if D > 1 else P["qpath"]
-    dlo, dhi = 0, len(mine)
     cell = V.read_cell(P["nbr"], n, P["pos"], b["x_min"], b["x_max"], b["y_min"], b["y_max"])
     sites = V.VoronoiSites(*cell, atm["temperature"], atm["electron_density"], atm["hydrogen_density"], atm["velocity_z"],
                            atm["velocity_x"], atm["velocity_y"], b["z_min"], b["z_max"], b["x_min"], b["x_max"], b["y_min"], b["y_max"], n)
     ndirs = int(np.sum(th != 90))
+    mine = assign_directions(sites, w, th, ph, D, di)
+    my_quad = (w[mine], th[mine], ph[mine]) if D > 1 else P["qpath"]
+    dlo, dhi = 0, len(mine)
     solver = V.Solver(sites, my_quad, line=line, α_cont=α_cont, ελ=ελ, C_rates=Cr, LTE_pops=lte,
                       lam_range=(lo, hi) if G > 1 else None, dir_range=(dlo, dhi) if D > 1 else None,
                       cell_shard=(di, D) if D > 1 and not os.environ.get("VRT_NO_CELL_SHARD") else None)
     coll = {"ms": 0.0, "bytes": 0}
+    comm_how = None
     if world > 1:
-        class _Dev:
-            def __init__(self, ptr, count):
-                self.__cuda_array_interface__ = {"shape": (count,), "typestr": "<f8", "data": (ptr, False), "version": 3}
-
-        # process groups: ranks sharing a direction shard (they differ in wavelength shard) and vice versa
-        lam_groups = [dist.new_group([g * D + d for g in range(G)]) for d in range(D)]
-        dir_groups = [dist.new_group([g * D + d for d in range(D)]) for g in range(G)]
-
-        def allreduce(ptr, count, op):
-            if op == 0 and G == 1:
-                return 0        # the rates are already complete: this rank holds every wavelength
-            if op == 2 and D == 1:
-                return 0
-            t = torch.as_tensor(_Dev(ptr, count), device=torch.device("cuda", local_rank))
-            t0c = time.perf_counter()
-            if op in (3, 4):      # cell slices over the direction group: slice `di` of D equal slices is this rank's
-                sl = t[di * (count // D):(di + 1) * (count // D)]
-                if op == 3:
-                    dist.reduce_scatter_tensor(sl, t, op=dist.ReduceOp.SUM, group=dir_groups[gi])
-                else:
-                    dist.all_gather_into_tensor(t, sl, group=dir_groups[gi])
-                torch.cuda.synchronize()
-                coll["ms"] += 1e3 * (time.perf_counter() - t0c)
-                coll["bytes"] += 8 * count
-                return 0
-            if op == 1:
-                dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            elif op == 0:
-                dist.all_reduce(t, op=dist.ReduceOp.SUM, group=lam_groups[di])
-            else:
-                dist.all_reduce(t, op=dist.ReduceOp.SUM, group=dir_groups[gi])
-            torch.cuda.synchronize()
-            coll["ms"] += 1e3 * (time.perf_counter() - t0c)
-            coll["bytes"] += 8 * count
-            return 0
-        solver.set_allreduce(allreduce)
-    log(f"setup {time.time() - t_setup:.1f}s: n={n} dirs={ndirs} nlam={nlam} shards: {D} direction x {G} wavelength; rank 0 has directions {mine} wavelengths [{lo},{hi}) layers up/down={len(sites.layers_up) - 1}/{len(sites.layers_down) - 1}")
+        comm_how = attach_collectives(solver, dist, torch, local_rank, rank, world, D, G, di, gi, coll)
+    log(f"setup {time.time() - t_setup:.1f}s: n={n} dirs={ndirs} nlam={nlam} shards: {D} direction x {G} wavelength; rank 0 has directions {list(mine)} wavelengths [{lo},{hi}) layers up/down={len(sites.layers_up) - 1}/{len(sites.layers_down) - 1}")
 
     def sync():
         torch.cuda.synchronize()
@@ -337,6 +411,8 @@ def main():
     ms = e0.elapsed_time(e1)
     stats = _lib.last_stats()
     hist = res["history"]
+    checksum = solver.checksum()          # after W + K iterations from S = B, populations = LTE: must agree for every N
+    checksum["iterations"] = W + K
     coll_ms, coll_bytes = coll["ms"] / K, coll["bytes"] / K
     tt = torch.tensor([ms, stats["sweep_ms"]], dtype=torch.float64, device="cuda")
     if dist is not None:
@@ -358,37 +434,51 @@ def main():
             traffic = json.load(open(tf)).get(args.workload)
         except Exception:
             traffic = None
-    roofline = {"bound": "hbm", "kernel": "k_sweep", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+    roofline = {"bound": "hbm", "kernel": "k_sweep_tma", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_update": B_alg,
                 "sweep_ms_per_step": sweep_ms_max / K, "sweep_share_of_step": sweep_ms_max / ms_max,
+                "whole_step_frac": B_alg * updates_total / (ms_max / K / 1e3) / 1e9 / peak / world,
                 "cell_visits_per_step": stats["visits"] / K * (1.0), "dependent_steps_per_step": stats["steps"] / K}
 
     # ---- end to end through the C ABI with pinned host buffers: state in, one Λ-iteration, S/J/populations out
     # Per step: S and populations go host -> device (restart state, like recover_simulation.jl), one Λ-iteration runs, and S and
     # populations come back device -> host (what the reference writes to its HDF5 file after every iteration,
-    # lambda_iteration.jl:280-281).
+    # lambda_iteration.jl:280-281).  With cell shards (N > 1) every rank moves only its own cell slice of S and of the
+    # populations: the slices of the other ranks arrive through the all-gather the iteration does anyway.
     e2e = None
     dt_local = float("inf")
     nl = hi - lo
+    sliced = D > 1 and not os.environ.get("VRT_NO_CELL_SHARD") and not os.environ.get("VRT_E2E_FULL")
+    c0, c1 = solver.cell_slice() if sliced else (0, n)
+    ncell = c1 - c0
     try:
         if args.no_e2e:
             raise StopIteration
         import ctypes as C
         L = _lib.lib()
-        hS = torch.empty((n, nl), dtype=torch.float64).pin_memory()
-        hP = torch.empty((3, n), dtype=torch.float64).pin_memory()
-        _lib.check(L.vrt_get_state(solver.h, C.c_void_p(hS.data_ptr()), None, C.c_void_p(hP.data_ptr())))
+        hS = torch.empty((ncell, nl), dtype=torch.float64).pin_memory()
+        hP = torch.empty((3, ncell), dtype=torch.float64).pin_memory()
+        if sliced:
+            _lib.check(L.vrt_get_state_slice(solver.h, C.c_void_p(hS.data_ptr()), None, C.c_void_p(hP.data_ptr())))
+        else:
+            _lib.check(L.vrt_get_state(solver.h, C.c_void_p(hS.data_ptr()), None, C.c_void_p(hP.data_ptr())))
 
         null_cb = _abi_null_cb()
         dbg = os.environ.get("VRT_DEBUG")
 
         def step():
             ta = time.perf_counter()
-            _lib.check(L.vrt_set_state(solver.h, C.c_void_p(hS.data_ptr()), C.c_void_p(hP.data_ptr())))
+            if sliced:
+                _lib.check(L.vrt_set_state_slice(solver.h, C.c_void_p(hS.data_ptr()), C.c_void_p(hP.data_ptr())))
+            else:
+                _lib.check(L.vrt_set_state(solver.h, C.c_void_p(hS.data_ptr()), C.c_void_p(hP.data_ptr())))
             tb = time.perf_counter()
             _lib.check(L.vrt_lambda_iterate(solver.h, -1.0, 1, null_cb, None, None))
             tc = time.perf_counter()
-            _lib.check(L.vrt_get_state(solver.h, C.c_void_p(hS.data_ptr()), None, C.c_void_p(hP.data_ptr())))
+            if sliced:
+                _lib.check(L.vrt_get_state_slice(solver.h, C.c_void_p(hS.data_ptr()), None, C.c_void_p(hP.data_ptr())))
+            else:
+                _lib.check(L.vrt_get_state(solver.h, C.c_void_p(hS.data_ptr()), None, C.c_void_p(hP.data_ptr())))
             if dbg:
                 log(f"e2e step: set_state {1e3 * (tb - ta):.1f} ms, iterate {1e3 * (tc - tb):.1f} ms, get_state {1e3 * (time.perf_counter() - tc):.1f} ms")
         for _ in range(2):
@@ -410,40 +500,411 @@ def main():
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dt = float(tt[0])
         if np.isfinite(dt):
-            e2e = {"value": updates_total / (dt / K), "unit": "updates/s", "h2d_bytes_per_step": int(8 * (n * nl + 3 * n)),
-                   "d2h_bytes_per_step": int(8 * (n * nl + 3 * n)), "ms_per_step": 1e3 * dt / K,
-                   "api": "vrt_set_state(S, populations) + vrt_lambda_iterate(1 iteration) + vrt_get_state(S, populations) with pinned host buffers; best of 2 repetitions of K steps"}
+            per_rank = int(8 * (ncell * nl + 3 * ncell))
+            e2e = {"value": updates_total / (dt / K), "unit": "updates/s", "h2d_bytes_per_step": per_rank * (world if sliced else 1),
+                   "d2h_bytes_per_step": per_rank * (world if sliced else 1), "ms_per_step": 1e3 * dt / K,
+                   "api": ("vrt_set_state_slice + vrt_lambda_iterate(1 iteration) + vrt_get_state_slice: every rank moves its own cell slice of S and the populations "
+                           "through pinned host buffers (bytes are the sum over ranks)" if sliced else
+                           "vrt_set_state(S, populations) + vrt_lambda_iterate(1 iteration) + vrt_get_state(S, populations) with pinned host buffers")
+                          + "; best of 2 repetitions of K steps"}
 
-    # ---- CPU baseline beside it (rank 0, N = 1 only): bounded sample of the same workload
+    # ---- CPU baseline beside it (rank 0, N = 1 only): bounded sample of the same workload, and the CUDA path checked
+    # against it on exactly that sample (parity at the benchmark's own size)
     cpu = None
+    parity = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        solver.close()      # free the work buffers: the parity solve below needs its own
+        solver = None
         threads = os.cpu_count() or 1
-        run, info = cpu_reference_sample(P, line, (lte, α_cont, ελ, Cr), threads)
+        inputs = (lte, α_cont, ελ, Cr)
+        run, info = cpu_reference_sample(P, line, inputs, threads, keep_J=True)
         t = run()
-        cpu = {"value": info["n"] * info["ndirs"] * info["nlam_sample"] / t, "unit": "updates/s", "cores": info["threads"], "kind": "port",
+        upd = info["n"] * info["ndirs"] * info["nlam_sample"]
+        cpu = {"value": upd / t, "unit": "updates/s", "cores": info["threads"], "kind": "port",
                "sample": f"{info['nlam_sample']} of {nlam} wavelengths x the first {info['ndirs']} of {int(nq)} directions x {info['n']} sites, one formal solution "
-                         f"({t:.1f} s), stencil recomputed per visit like the reference; C/OpenMP port (Julia not installed)"}
-        if n <= 4_000_000:   # second flavour (stencil hoisted out of the wavelength loop: the fairer CPU bar); skipped on huge grids
-            run_h, _ = cpu_reference_sample(P, line, (lte, α_cont, ελ, Cr), threads, hoist=1)
-            th_ = run_h()
-            cpu["hoisted_value"] = info["n"] * info["ndirs"] * info["nlam_sample"] / th_
+                         f"({t:.1f} s), stencil recomputed per visit like the reference (faithful); C/OpenMP port (Julia not installed), -O3 -march=native"}
+        try:
+            parity = gpu_parity_on_sample(V, sites, P, line, inputs, info)
+        except Exception as ex:  # noqa: BLE001
+            parity = {"error": str(ex)}
+        # second flavour: stencil hoisted out of the wavelength loop (the fairer CPU bar)
+        run_h, _ = cpu_reference_sample(P, line, inputs, threads, hoist=1)
+        th_ = run_h()
+        cpu["hoisted_value"] = upd / th_
+        cpu["hoisted_note"] = f"same sample with the upwind stencil computed once per direction ({th_:.1f} s)"
 
     if rank == 0:
-        out = {"metric": "cell*angle*freq updates/s per formal solution (NLTE Lambda-iteration)", "value": value, "unit": "updates/s",
+        out = {"metric": METRIC, "value": value, "unit": "updates/s",
                "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "strong",
                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                "config": {"workload": workload_name(args.workload, P, nlam), "sites": n, "quadrature": P["qname"], "n_dirs": ndirs, "n_lambda": nlam,
-                          "parallelism": f"{D} direction shards x {G} wavelength shards, NCCL reduce-scatter of J + all-gather of S ({8 * n * (hi - lo) / 1e6:.0f} MB each) per iteration; source update, rates and statistical equilibrium sharded over cells" if world > 1 else "single GPU", "l2_policy": "inputs larger than L2 "
-                          f"(S+J+I+alpha = {8 * n * nlam * (2 + 2 * ndirs) / 1e9:.1f} GB)", "n_sweeps": 3, "p": 7.0},
-               "s_per_lambda_iteration": ms_max / K / 1e3, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
-               "gpu_launches": int(launches), "clocks": clocks,
-               "collectives": {"ms_per_step": coll_ms, "bytes_per_step": coll_bytes, "what": "NCCL reduce-scatter of J + all-gather of S and populations over the direction shards, max of the criterion" if world > 1 else None},
+                          "parallelism": f"{D} direction shards x {G} wavelength shards; {comm_how}" if world > 1 else "single GPU", "l2_policy": "inputs larger than L2 "
+                          f"(S+J+I+alpha = {8 * n * nlam * (2 + 2 * ndirs) / 1e9:.1f} GB)", "n_sweeps": 3, "p": 7.0,
+                          "visit_order": os.environ.get("VRT_BLOCKS", "default") + "/" + os.environ.get("VRT_SLAB", "default")},
+               "s_per_lambda_iteration": ms_max / K / 1e3, "roofline": roofline, "cpu_baseline": cpu, "parity": parity, "checksum": checksum,
+               "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+               "collectives": {"ms_per_step": coll_ms, "bytes_per_step": coll_bytes, "how": comm_how, "nccl_log": nccl_log} if world > 1 else None,
                "stage_ms": {k: float(np.mean([h[k] for h in hist])) for k in ("t_opacity_ms", "t_sweep_ms", "t_source_ms", "t_rates_ms", "t_stateq_ms", "t_total_ms")} if hist else None}
         print(json.dumps(out))
-    solver.close()
+    if solver is not None:
+        solver.close()
     if dist is not None:
         dist.destroy_process_group()
     return 0
+
+
+def assign_directions(sites, w, th, ph, D, di):
+    """directions of rank di of D direction shards.  Round-robin deal (rank di takes di, di+D, ...): neighbouring lines of the
+    quadrature files are up/down pairs of similar inclination, so every rank gets a similar mix of steep and grazing rays."""
+    nq = len(w)
+    if D <= 1:
+        return np.arange(nq)
+    return np.arange(di, nq, D)
+
+
+def attach_collectives(solver, dist, torch, local_rank, rank, world, D, G, di, gi, coll):
+    """N > 1: the collectives of the Λ-iteration.  Preferred: inside the library (vrt_solver_comm_init: ncclCommInitRank from a
+    unique id broadcast here, reduce-scatter / all-gather / all-reduce issued by libvrt.so on its own stream).  Fallback
+    (VRT_HOST_COLLECTIVES=1 or a library built without NCCL): the round-1 host hook through torch.distributed."""
+    import ctypes as C
+    from voronoirt_b200 import _lib
+    L = _lib.lib()
+    if not os.environ.get("VRT_HOST_COLLECTIVES") and L.vrt_nccl_available() == 1:
+        from voronoirt_b200 import api
+
+        def group_id(members):
+            """a unique id made by the first member, broadcast to the others (torch.distributed only ferries 128 bytes)"""
+            grp = dist.new_group(members)          # every rank must take part in every new_group call
+            buf = torch.zeros(128, dtype=torch.uint8, device="cuda")
+            if rank == members[0]:
+                buf = torch.frombuffer(bytearray(api.nccl_unique_id()), dtype=torch.uint8).cuda()
+            if rank in members:
+                dist.broadcast(buf, src=members[0], group=grp)
+                return buf.cpu().numpy().tobytes()
+            return None
+        dir_id = lam_id = None
+        for g in range(G):
+            if D > 1:
+                r = group_id([g * D + d for d in range(D)])
+                dir_id = r if g == gi else dir_id
+        for d in range(D):
+            if G > 1:
+                r = group_id([g * D + d for g in range(G)])
+                lam_id = r if d == di else lam_id
+        solver.comm_init(dir_id, di, D, lam_id, gi, G)
+        return ("collectives inside libvrt.so (ncclCommInitRank from a broadcast unique id, own stream): reduce-scatter of J, all-gather of S and the "
+                "populations, all-reduce of the rates over wavelength shards, max of the criterion; source update, rates and statistical equilibrium sharded over cells")
+
+    class _Dev:
+        def __init__(self, ptr, count):
+            self.__cuda_array_interface__ = {"shape": (count,), "typestr": "<f8", "data": (ptr, False), "version": 3}
+
+    # process groups: ranks sharing a direction shard (they differ in wavelength shard) and vice versa
+    lam_groups = [dist.new_group([g * D + d for g in range(G)]) for d in range(D)]
+    dir_groups = [dist.new_group([g * D + d for d in range(D)]) for g in range(G)]
+
+    def allreduce(ptr, count, op):
+        if op == 0 and G == 1:
+            return 0        # the rates are already complete: this rank holds every wavelength
+        if op == 2 and D == 1:
+            return 0
+        t = torch.as_tensor(_Dev(ptr, count), device=torch.device("cuda", local_rank))
+        t0c = time.perf_counter()
+        if op in (3, 4):      # cell slices over the direction group: slice `di` of D equal slices is this rank's
+            sl = t[di * (count // D):(di + 1) * (count // D)]
+            if op == 3:
+                dist.reduce_scatter_tensor(sl, t, op=dist.ReduceOp.SUM, group=dir_groups[gi])
+            else:
+                dist.all_gather_into_tensor(t, sl, group=dir_groups[gi])
+        elif op == 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elif op == 0:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=lam_groups[di])
+        else:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=dir_groups[gi])
+        torch.cuda.synchronize()
+        coll["ms"] += 1e3 * (time.perf_counter() - t0c)
+        coll["bytes"] += 8 * count
+        return 0
+    solver.set_allreduce(allreduce)
+    return "host hook: torch.distributed NCCL reduce-scatter of J + all-gather of S and the populations per iteration (vrt_solver_set_allreduce)"
+
+
+def _libvrt_mapped():
+    try:
+        return "libvrt.so" in open("/proc/self/maps").read()
+    except OSError:
+        return None
+
+
+def _line(out):
+    if out.get("impl") == "reference":
+        out["libvrt_mapped"] = _libvrt_mapped()     # the CPU arm must not touch the product library
+    print(json.dumps(out))
+    return 0
+
+
+def main_continuum(args, W, K):
+    """BASELINE configs[1]: continuum Λ-iteration (Λ_voronoi of lambda_continuum.jl:109-160) on 1 M sites, ul7n12, one
+    wavelength.  A step is one Λ-iteration: 12 formal solutions, S = (1-ε)J + εB, criterion.  N > 1: replicas only."""
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if rank != 0:
+        return 0
+    from voronoirt_b200 import api, synth
+    metric = "cell*angle*freq updates/s per formal solution (continuum Lambda-iteration)"
+    B_alg = 144.0     # 40 + 104/nλ with nλ = 1 (SURVEY §8d)
+    cpu_arm = args.impl == "reference"
+    P = build_problem(args.workload, cpu_arm=cpu_arm)
+    atm, b, n = P["atm"], P["bounds"], P["n"]
+    α, ε, B0 = synth.continuum_inputs(atm["temperature"], atm["electron_density"], atm["hydrogen_density"])
+    w, th, ph, nq = api.read_quadrature(P["qpath"])
+    ndirs = int(np.sum(th != 90))
+    updates = float(n) * ndirs
+    wname = (f"{args.workload}: continuum Lambda-iteration (500 nm), {WORKLOADS[args.workload][0]} Voronoi sites sampled from the synthetic Bifrost-shaped atmosphere, "
+             f"{P['qname']}, one wavelength")
+
+    def cpu_leg():
+        O = _oracle()
+        threads = O.set_num_threads(os.cpu_count() or 1)
+        bounds = [b["z_min"], b["z_max"], b["x_min"], b["x_max"], b["y_min"], b["y_max"]]
+        osites = O.Sites(np.ascontiguousarray(P["pos"].T), np.ascontiguousarray(P["nbr"].T), bounds)
+        oq = O.make_quadrature(w, th, ph)
+        box = {}
+
+        def run():
+            t = time.perf_counter()
+            box["J"] = O.J_continuum(osites, oq, B0, α, B0, hoist=0)
+            return time.perf_counter() - t
+        return run, threads, box
+
+    if cpu_arm:
+        run, threads, _ = cpu_leg()
+        for _ in range(min(W, 1)):
+            run()
+        t = float(np.mean([run() for _ in range(K)]))
+        val = updates / t
+        sample = (f"one J_λ_voronoi (all {ndirs} directions, serial over directions like lambda_continuum.jl:40; one wavelength so one thread does the work) on {n} sites"
+                  + (f" (spatial sample: {P['spatial_sample']}, voro++ tessellation)" if P.get("spatial_sample") else "") + "; C port of the Julia reference, -O3 -march=native")
+        return _line({"impl": "reference", "metric": metric, "value": val, "unit": "updates/s", "n_gpus": args.gpus, "steps": K, "warmup": min(W, 1),
+                      "ms_per_step": 1e3 * t, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                      "config": {"workload": wname},
+                      "cpu_baseline": {"value": val, "unit": "updates/s", "cores": 1, "kind": "port", "sample": sample},
+                      "e2e": {"value": val, "unit": "updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+
+    import torch
+    import voronoirt_b200 as V
+    from voronoirt_b200 import _lib
+    import ctypes as C
+    torch.cuda.set_device(0)
+    cell = V.read_cell(P["nbr"], n, P["pos"], b["x_min"], b["x_max"], b["y_min"], b["y_max"])
+    sites = V.VoronoiSites(*cell, atm["temperature"], atm["electron_density"], atm["hydrogen_density"], atm["velocity_z"],
+                           atm["velocity_x"], atm["velocity_y"], b["z_min"], b["z_max"], b["x_min"], b["x_max"], b["y_min"], b["y_max"], n)
+    solver = V.Solver(sites, P["qpath"], α_cont=α, ελ=ε, B_0=B0)
+    solver.iterate(-1.0, W)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(0)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    res = solver.iterate(-1.0, K)
+    e1.record()
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    ms = e0.elapsed_time(e1)
+    stats = _lib.last_stats()
+    checksum = solver.checksum()
+    peak, peak_src = measured_peak()
+    achieved = B_alg * updates * K / (stats["sweep_ms"] / 1e3) / 1e9 if stats["sweep_ms"] > 0 else 0.0
+    roofline = {"bound": "hbm", "kernel": "k_sweep (register path, rows of one double)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_update": B_alg,
+                "sweep_ms_per_step": stats["sweep_ms"] / K, "sweep_share_of_step": stats["sweep_ms"] / ms,
+                "note": "latency-bound: a row is a single double, the working set (1 M sites x a few arrays) sits in L2"}
+    # e2e: S in from pinned host memory, one Λ-iteration, S and J back out
+    e2e = None
+    if not args.no_e2e:
+        L = _lib.lib()
+        hS = torch.empty(n, dtype=torch.float64).pin_memory()
+        hJ = torch.empty(n, dtype=torch.float64).pin_memory()
+        _lib.check(L.vrt_get_state(solver.h, C.c_void_p(hS.data_ptr()), None, None))
+        cb = _abi_null_cb()
+
+        def step():
+            _lib.check(L.vrt_set_state(solver.h, C.c_void_p(hS.data_ptr()), None))
+            _lib.check(L.vrt_lambda_iterate(solver.h, -1.0, 1, cb, None, None))
+            _lib.check(L.vrt_get_state(solver.h, C.c_void_p(hS.data_ptr()), C.c_void_p(hJ.data_ptr()), None))
+        step()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(K):
+            step()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        e2e = {"value": updates / (dt / K), "unit": "updates/s", "h2d_bytes_per_step": 8 * n, "d2h_bytes_per_step": 16 * n, "ms_per_step": 1e3 * dt / K,
+               "api": "vrt_set_state(S) + vrt_lambda_iterate(1 iteration) + vrt_get_state(S, J) with pinned host buffers"}
+    cpu = parity = None
+    if not args.no_cpu_baseline:
+        run, threads, box = cpu_leg()
+        t = run()
+        cpu = {"value": updates / t, "unit": "updates/s", "cores": 1, "kind": "port",
+               "sample": f"one J_λ_voronoi of the same workload: all {ndirs} directions x {n} sites ({t:.1f} s); serial like lambda_continuum.jl:40 (one wavelength: nothing to thread over)"}
+        Jg = solver.mean_intensity(B0, J=np.zeros(n))
+        Jo = box["J"]
+        parity = {"what": f"J of one J_λ_voronoi call ({ndirs} directions x {n} sites, S = B_0): CUDA path against the CPU oracle",
+                  "max_rel_err": float(np.abs(Jg - Jo).max() / np.abs(Jo).max()), "tolerance": 1e-9}
+        parity["ok"] = parity["max_rel_err"] <= 1e-9
+    solver.close()
+    hist = res["history"]
+    return _line({"metric": metric, "value": updates / (ms / K / 1e3), "unit": "updates/s", "n_gpus": 1, "steps": K, "warmup": W, "ms_per_step": ms / K,
+                  "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                  "config": {"workload": wname, "sites": n, "quadrature": P["qname"], "n_dirs": ndirs, "n_lambda": 1,
+                             "parallelism": "single GPU" if world == 1 else "replicas only (rank 0 reports)",
+                             "l2_policy": "working set smaller than L2 by nature of the workload (8 MB per array); 12 directions x 3 sweeps touch every array between two uses of a row"},
+                  "s_per_lambda_iteration": ms / K / 1e3, "roofline": roofline, "cpu_baseline": cpu, "parity": parity, "checksum": checksum, "e2e": e2e,
+                  "gpu_launches": int(max(stats["kernels"], 1)), "clocks": clocks,
+                  "stage_ms": {k: float(np.mean([h[k] for h in hist])) for k in ("t_opacity_ms", "t_sweep_ms", "t_source_ms", "t_total_ms")} if hist else None})
+
+
+def main_searchlight(args, W, K):
+    """BASELINE configs[0]: searchlight beam test (compare_searchlight.jl:10-152): 51^3 uniform sites in the unit box, S = 0,
+    α = 0, I_0 = 1 inside a disk of radius 0.1 on the boundary layer, the ul7n12 directions one at a time with p = 7.
+    A step is the 12 formal solutions (Delaunay_upII / Delaunay_downII), each a separate call like the reference's loop."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from voronoirt_b200 import api
+    metric = "cell*angle*freq updates/s per formal solution (searchlight)"
+    cpu_arm = args.impl == "reference"
+    P = build_problem(args.workload, cpu_arm=cpu_arm)
+    n, b = P["n"], P["bounds"]
+    w, th, ph, nq = api.read_quadrature(P["qpath"])
+    dirs = [(t, p) for t, p in zip(th, ph) if t != 90]
+    updates = float(n) * len(dirs)
+    wname = f"searchlight: {n} uniform Voronoi sites (51^3, unit box), S = 0, alpha = 0, unit beam of radius 0.1, the {len(dirs)} directions of {P['qname']} one at a time, p = 7"
+    R0 = 0.1
+
+    def boundary(pos, perm, n1):
+        c = perm[:n1] - 1
+        return (((pos[1, c] - 0.5) ** 2 + (pos[2, c] - 0.5) ** 2) < R0 ** 2).astype(np.float64)
+
+    def cpu_leg():
+        O = _oracle()
+        bounds = [b["z_min"], b["z_max"], b["x_min"], b["x_max"], b["y_min"], b["y_max"]]
+        osites = O.Sites(np.ascontiguousarray(P["pos"].T), np.ascontiguousarray(P["nbr"].T), bounds)
+        lay = [osites.layers(0), osites.layers(1)]
+        box = {}
+
+        def run():
+            t = time.perf_counter()
+            out = []
+            for (t_, p_) in dirs:
+                k = api.direction(t_, p_)
+                down = int(t_ < 90)
+                perm, off = lay[down]
+                I0 = boundary(P["pos"], perm, off[1] - 1)
+                out.append(osites.formal_solve(k, down, np.zeros(n), np.zeros(n), I0, hoist=0)[:, 0])
+            box["I"] = out
+            return time.perf_counter() - t
+        return run, box
+
+    if cpu_arm:
+        run, _ = cpu_leg()
+        for _ in range(min(W, 1)):
+            run()
+        t = float(np.mean([run() for _ in range(K)]))
+        val = updates / t
+        return _line({"impl": "reference", "metric": metric, "value": val, "unit": "updates/s", "n_gpus": args.gpus, "steps": K, "warmup": min(W, 1),
+                      "ms_per_step": 1e3 * t, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                      "config": {"workload": wname},
+                      "cpu_baseline": {"value": val, "unit": "updates/s", "cores": 1, "kind": "port",
+                                       "sample": "the whole workload (12 directions, one thread: the reference's searchlight loop is serial); C port of Delaunay_upII/downII"},
+                      "e2e": {"value": val, "unit": "updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+
+    import torch
+    import voronoirt_b200 as V
+    from voronoirt_b200 import _lib
+    import ctypes as C
+    torch.cuda.set_device(0)
+    cell = V.read_cell(P["nbr"], n, P["pos"], b["x_min"], b["x_max"], b["y_min"], b["y_max"])
+    z = np.zeros(n)
+    sites = V.VoronoiSites(*cell, z, z, z, z, z, z, b["z_min"], b["z_max"], b["x_min"], b["x_max"], b["y_min"], b["y_max"], n)
+    L = _lib.lib()
+    gh = sites._grid.h
+    work = []
+    for (t_, p_) in dirs:
+        k = np.ascontiguousarray(api.direction(t_, p_))
+        down = int(t_ < 90)
+        perm = sites.perm_down if down else sites.perm_up
+        off = sites.layers_down if down else sites.layers_up
+        I0 = boundary(P["pos"], perm, off[1] - 1)
+        work.append((k, down, I0))
+    dS, dA = torch.zeros(n, dtype=torch.float64, device="cuda"), torch.zeros(n, dtype=torch.float64, device="cuda")
+    dI = torch.empty(n, dtype=torch.float64, device="cuda")
+    dI0 = [torch.from_numpy(I0).cuda() for (_, _, I0) in work]
+    hS, hA = torch.zeros(n, dtype=torch.float64).pin_memory(), torch.zeros(n, dtype=torch.float64).pin_memory()
+    hI = torch.empty(n, dtype=torch.float64).pin_memory()
+
+    def step_dev():
+        for (k, down, _), i0 in zip(work, dI0):
+            _lib.check(L.vrt_formal_solve(gh, C.c_void_p(k.ctypes.data), down, 7.0, 3, 1, C.c_void_p(dS.data_ptr()), C.c_void_p(dA.data_ptr()),
+                                          C.c_void_p(i0.data_ptr()), C.c_void_p(dI.data_ptr())))
+
+    def step_host(keep=None):
+        for (k, down, I0) in work:
+            _lib.check(L.vrt_formal_solve(gh, C.c_void_p(k.ctypes.data), down, 7.0, 3, 1, C.c_void_p(hS.data_ptr()), C.c_void_p(hA.data_ptr()),
+                                          C.c_void_p(I0.ctypes.data), C.c_void_p(hI.data_ptr())))
+            if keep is not None:
+                keep.append(hI.numpy().copy())
+    for _ in range(W):
+        step_dev()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(0)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sweep_ms, launches = 0.0, 0
+    e0.record()
+    for _ in range(K):
+        for (k, down, _), i0 in zip(work, dI0):
+            _lib.check(L.vrt_formal_solve(gh, C.c_void_p(k.ctypes.data), down, 7.0, 3, 1, C.c_void_p(dS.data_ptr()), C.c_void_p(dA.data_ptr()),
+                                          C.c_void_p(i0.data_ptr()), C.c_void_p(dI.data_ptr())))
+            st = _lib.last_stats()
+            sweep_ms += st["sweep_ms"]
+            launches += int(st["kernels"])
+    e1.record()
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    ms = e0.elapsed_time(e1)
+    step_host()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        step_host()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    peak, peak_src = measured_peak()
+    B_alg = 144.0
+    achieved = B_alg * updates * K / (sweep_ms / 1e3) / 1e9 if sweep_ms > 0 else 0.0
+    roofline = {"bound": "hbm", "kernel": "k_sweep (register path, rows of one double)", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_update": B_alg, "sweep_ms_per_step": sweep_ms / K,
+                "sweep_share_of_step": sweep_ms / ms, "note": "133 k sites x one wavelength: launch- and latency-bound, the whole grid sits in L2"}
+    e2e = {"value": updates / (dt / K), "unit": "updates/s", "h2d_bytes_per_step": int(len(dirs) * 8 * (2 * n + n // 50)), "d2h_bytes_per_step": int(len(dirs) * 8 * n),
+           "ms_per_step": 1e3 * dt / K, "api": "vrt_formal_solve per direction with HOST buffers (S, alpha, I_0 in; I out), like the reference's loop over Delaunay_upII / Delaunay_downII"}
+    cpu = parity = None
+    if not args.no_cpu_baseline:
+        run, box = cpu_leg()
+        t = run()
+        cpu = {"value": updates / t, "unit": "updates/s", "cores": 1, "kind": "port", "sample": f"the whole workload, serial like the reference's searchlight loop ({t:.1f} s)"}
+        got = []
+        step_host(got)
+        err = max(float(np.abs(g - o).max()) for g, o in zip(got, box["I"]))
+        # the beam keeps its unit amplitude scale (0 <= I <= 1): absolute = relative to max I_0
+        parity = {"what": f"I of all {len(dirs)} directions x {n} sites: CUDA path (vrt_formal_solve, host buffers) against the CPU oracle", "max_abs_err_over_max_I0": err,
+                  "tolerance": 1e-9, "ok": err <= 1e-9}
+    return _line({"metric": metric, "value": updates / (ms / K / 1e3), "unit": "updates/s", "n_gpus": 1, "steps": K, "warmup": W, "ms_per_step": ms / K,
+                  "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                  "config": {"workload": wname, "sites": n, "quadrature": P["qname"], "n_dirs": len(dirs), "n_lambda": 1, "parallelism": "single GPU (replicas only for N > 1)",
+                             "l2_policy": "the workload is smaller than L2 by definition (133 k sites); every step rewrites all of I"},
+                  "roofline": roofline, "cpu_baseline": cpu, "parity": parity, "e2e": e2e, "gpu_launches": launches // max(K, 1), "clocks": clocks})
 
 
 def regular_problem(nz, nx, ny, nbb, nbf):

@@ -284,6 +284,23 @@ int vrt_solver_create_continuum(vrt_grid* g, const double* alpha_cont, const dou
                                 const vrt_quadrature* quad, const vrt_config* cfg, vrt_solver** out);
 void vrt_solver_destroy(vrt_solver* s);
 int vrt_solver_set_allreduce(vrt_solver* s, vrt_allreduce_fn fn, void* user);
+/* Collectives inside the library (preferred over the hook above; north star (5): "NCCL allreduce over NVLink").  One process
+ * per GPU.  The host creates a unique id with vrt_nccl_unique_id on ONE process of a group, ferries its 128 bytes to the
+ * others with whatever it has (MPI, sockets, a file, torch.distributed — no NCCL binding needed on the host side) and every
+ * member calls vrt_solver_comm_init; the library then does ncclCommInitRank itself and issues the reduce-scatter of J, the
+ * all-gather of S and the populations, the all-reduce of the rates and the max of the criterion on its own stream.
+ *   dir group: the processes that share a wavelength shard and differ in direction shard (ops 2, 3, 4 of the hook);
+ *              dir_rank / dir_size must equal vrt_config.cell_shard_rank / cell_shard_count when cell shards are used;
+ *   lam group: the processes that share a direction shard and differ in wavelength shard (op 0).
+ * A group of size <= 1 takes a NULL id.  NCCL is bound at run time (libnccl.so.2, or $VRT_NCCL_LIB); vrt_nccl_available() is 0
+ * when it cannot be loaded, and these calls then return VRT_E_STATE.  The independence being exploited is
+ * lambda_iteration.jl:84-110 (every direction and wavelength is a separate formal solution). */
+int vrt_nccl_available(void);
+int vrt_nccl_version(int32_t* version);
+int vrt_nccl_unique_id(char id[128]);
+int vrt_solver_comm_init(vrt_solver* s, const char* dir_id, int32_t dir_rank, int32_t dir_size,
+                         const char* lam_id, int32_t lam_rank, int32_t lam_size);
+
 /* (Re)upload one per-site input of the line solver.  In the reference these are plain function arguments
  * (α_cont of J_λ_voronoi, LTE_pops of calculate_R, C of get_revised_populations), so a drop-in caller may
  * hand them over late or change them between calls.  Shapes as in vrt_site_data. */
@@ -312,6 +329,21 @@ int vrt_lambda_iterate(vrt_solver* s, double eps, int32_t maxiter, vrt_iter_cb c
  * S, J nlam_local x n; populations n x 3. */
 int vrt_get_state(vrt_solver* s, double* S, double* J, double* populations);
 int vrt_set_state(vrt_solver* s, const double* S, const double* populations);
+
+/* Cell-sliced checkpoint hooks for the multi-GPU solve.  With cell shards every process owns the source function, the mean
+ * intensity and the populations of the cells [first, last) in the library's INTERNAL cell order — internal cell c is site
+ * perm_up[c] (vrt_grid_get_layers, down = 0) — and only that slice crosses its PCIe link: S, J are nlam_local x (last-first),
+ * populations (last-first) x 3.  vrt_set_state_slice is a collective call: the other processes' slices of S and of the
+ * populations arrive through the all-gather over NVLink.  Without cell shards the slice is all cells (in internal order). */
+int vrt_solver_cell_slice(const vrt_solver* s, int64_t* first, int64_t* last);
+int vrt_get_state_slice(vrt_solver* s, double* S, double* J, double* populations);
+int vrt_set_state_slice(vrt_solver* s, const double* S, const double* populations);
+
+/* Fingerprint of the device-resident state, reduced on the device (nothing the size of S crosses the bus):
+ * out[0] = Σ S, out[1] = max |S|, out[2] = Σ populations (0 for the continuum solver), out[3] = Σ J over the cells this
+ * process owns (all cells unless the post-J stages are cell-sharded).  Runs of the same problem on 1, 2, 4, 8 GPUs must agree
+ * in out[0..2] to rounding (the shards add the directions in another order). */
+int vrt_state_checksum(vrt_solver* s, double out[4]);
 
 /* counters of the last vrt_mean_intensity / vrt_formal_solve call on this thread's device:
  * out[0] kernels launched, out[1] cell visits, out[2] dependent steps, out[3] sweep-kernel ms (CUDA events) */

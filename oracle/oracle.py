@@ -18,15 +18,33 @@ from voronoirt_b200._abi import vrt_line, vrt_quadrature, vrt_site_data  # noqa:
 _LIB = None
 
 
+def _cpu_key():
+    """the oracle is compiled -march=native, so its file name carries the CPU it was built for"""
+    import hashlib
+    try:
+        txt = open("/proc/cpuinfo").read()
+        model = next((ln for ln in txt.splitlines() if ln.startswith("model name")), "")
+        flags = next((ln for ln in txt.splitlines() if ln.startswith("flags")), "")
+        return hashlib.sha1((model + flags).encode()).hexdigest()[:10]
+    except OSError:
+        return "generic"
+
+
+def lib_path():
+    return os.path.join(_HERE, f"libvrt_oracle_{_cpu_key()}.so")
+
+
 def build():
-    subprocess.run(["make", "-s", "-C", _HERE], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    subprocess.run(["make", "-s", "-C", _HERE, f"LIB={os.path.basename(lib_path())}"], check=True, stdout=subprocess.DEVNULL,
+                   stderr=subprocess.DEVNULL)
 
 
 def lib():
     global _LIB
     if _LIB is None:
-        path = os.path.join(_HERE, "libvrt_oracle.so")
-        if not os.path.exists(path):
+        path = lib_path()
+        src = [os.path.join(_HERE, f) for f in ("vrt_oracle.c", "vrt_oracle_regular.c")]
+        if not os.path.exists(path) or any(os.path.getmtime(f) > os.path.getmtime(path) for f in src):
             build()
         L = C.CDLL(path)
         L.orc_read_neighbours.restype = C.c_int64
@@ -231,6 +249,12 @@ def B_lambda(lam_nm, T):
 
 def num_threads():
     return lib().orc_num_threads()
+
+
+def set_num_threads(n):
+    """explicit OpenMP thread count (torchrun exports OMP_NUM_THREADS=1)"""
+    lib().orc_set_num_threads(C.c_int(int(n)))
+    return num_threads()
 
 
 def short_characteristics(z, x, y, k, down, S, I_0, alpha, n_sweeps=3):

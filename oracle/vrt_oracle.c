@@ -886,6 +886,15 @@ void orc_LTE_populations(const vrt_line* line, int64_t n, const double* T, const
     }
 }
 
+/* torchrun exports OMP_NUM_THREADS=1; the CPU baseline sets its thread count explicitly (JULIA_NUM_THREADS of the reference) */
+void orc_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 int orc_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

@@ -50,9 +50,10 @@ def quadrature_path(name):
 
 
 def default_voro_exec():
+    """the reference's voro++ driver: $VORO_EXEC, the reference tree, or the copy staged by baseline/Makefile"""
     here = os.path.dirname(os.path.abspath(__file__))
     for p in (os.environ.get("VORO_EXEC"), "/root/reference/rt_preprocessing/output_sites",
-              os.path.join(here, "..", "oracle", "_ref", "output_sites")):
+              os.path.join(here, "..", "baseline", "_ref", "output_sites")):
         if p and os.path.exists(p) and os.access(p, os.X_OK):
             return p
     return None
@@ -304,6 +305,13 @@ class VoronoiSites:
         self._grid = g
 
 
+def nccl_unique_id():
+    """128 bytes to be handed to every member of a process group (vrt_nccl_unique_id)"""
+    raw = C.create_string_buffer(128)
+    check(lib().vrt_nccl_unique_id(raw))
+    return raw.raw
+
+
 def direction(θ, ϕ):
     """k = [cos θ, cos ϕ sin θ, sin ϕ sin θ] on (z, x, y), degrees (src/lambda_iteration.jl:87)"""
     t, p = θ * np.pi / 180, ϕ * np.pi / 180
@@ -506,6 +514,29 @@ class Solver:
         self._ar = _abi.vrt_allreduce_fn(tramp)
         check(lib().vrt_solver_set_allreduce(self.h, self._ar, None))
 
+    def comm_init(self, dir_id=None, dir_rank=0, dir_size=1, lam_id=None, lam_rank=0, lam_size=1):
+        """in-library NCCL collectives (include/vrt.h vrt_solver_comm_init); ids are the 128 bytes of nccl_unique_id()"""
+        check(lib().vrt_solver_comm_init(self.h, dir_id, int(dir_rank), int(dir_size), lam_id, int(lam_rank), int(lam_size)))
+
+    def cell_slice(self):
+        """[first, last) of the cells this process owns, in internal order (site perm_up[c])"""
+        a, b = C.c_int64(), C.c_int64()
+        check(lib().vrt_solver_cell_slice(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def get_state_slice(self):
+        c0, c1 = self.cell_slice()
+        S = np.zeros((self.nlam, c1 - c0), order="F")
+        J = np.zeros((self.nlam, c1 - c0), order="F")
+        pops = np.zeros((c1 - c0, 3), order="F") if self.kind == "line" else None
+        check(lib().vrt_get_state_slice(self.h, _ptr(S), _ptr(J), _ptr(pops)))
+        return S, J, pops
+
+    def set_state_slice(self, S=None, populations=None):
+        S_ = None if S is None else _f(S)
+        P_ = None if populations is None else _f(populations)
+        check(lib().vrt_set_state_slice(self.h, _ptr(S_), _ptr(P_)))
+
     def mean_intensity(self, S, populations=None, J=None, damping=None):
         """J_λ_voronoi on host arrays or device tensors (any of S, populations, J, damping may be a torch CUDA tensor)."""
         if J is None:
@@ -540,6 +571,12 @@ class Solver:
         check(lib().vrt_lambda_iterate(self.h, float(ϵ), int(maxiter), self._cb, None, C.byref(res)))
         return {"iterations": res.iterations, "converged": bool(res.converged), "diff": res.diff, "seconds": res.seconds,
                 "history": history}
+
+    def checksum(self):
+        """device-side fingerprint of the state: ΣS, max|S|, Σ populations, ΣJ (own cells)"""
+        out = (C.c_double * 4)()
+        check(lib().vrt_state_checksum(self.h, out))
+        return {"sum_S": out[0], "max_abs_S": out[1], "sum_populations": out[2], "sum_J_own_cells": out[3]}
 
     def get_state(self):
         shape = (self.nlam, self.n) if self.kind == "line" else (self.n,)

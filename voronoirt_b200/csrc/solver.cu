@@ -9,6 +9,8 @@
 #include <algorithm>
 #include <array>
 #include <chrono>
+#include <cub/device/device_reduce.cuh>
+#include <cub/iterator/transform_input_iterator.cuh>
 #include "physics.cuh"
 #include "vrt_internal.h"
 
@@ -481,7 +483,7 @@ struct vrt_solver {
     bool dir_sharded = false;
     int cell_R = 1, cell_r = 0;             // cell shards of the post-J stages (source, rates, stat-eq)
     int64_t cs = 0, c0 = 0, c1 = 0, n_pad = 0; // cells per shard, own slice [c0, c1), padded cell count
-    DevBuf<double> pops_blk;
+    DevBuf<double> pops_blk, diff_pair;
     bool gamma_valid = false;
     // work buffers of the current (λ-chunk, direction-batch) plan
     int64_t lc = 0;
@@ -494,6 +496,9 @@ struct vrt_solver {
     DevBuf<int> diff_nan;
     vrt_allreduce_fn allreduce = nullptr;
     void* allreduce_user = nullptr;
+    void* comm = nullptr;                   // in-library NCCL communicators (comm.cu), preferred over the host hook
+    cudaEvent_t comm_ev[2] = {nullptr, nullptr};
+    bool has_exchange() const { return comm != nullptr || allreduce != nullptr; }
     // CUDA events are created once and reused (no create/destroy per iteration, nothing to leak on an early return)
     std::vector<cudaEvent_t> ev_pool;
     size_t ev_used = 0;
@@ -509,6 +514,9 @@ struct vrt_solver {
     ~vrt_solver() {
         for (auto* b : bufs) delete b;
         for (auto e : ev_pool) cudaEventDestroy(e);
+        for (auto e : comm_ev)
+            if (e) cudaEventDestroy(e);
+        if (comm) vrt::comm_free(comm);
     }
 };
 
@@ -695,6 +703,32 @@ static int plan_buffers(vrt_solver* s) {
     return VRT_OK;
 }
 
+// One exchange step between the processes (ops of vrt_allreduce_fn).  In-library NCCL: enqueued on the collectives' stream
+// between two events, so it is ordered after everything issued so far and before everything issued afterwards, without a
+// host synchronisation.  Host hook: the device is synchronised and the callback does the rest.
+static int exchange(vrt_solver* s, double* buf, int64_t count, int op) {
+    if (s->comm) {
+        cudaStream_t cs = comm_stream(s->comm);
+        for (auto& e : s->comm_ev)
+            if (!e) VRT_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        VRT_CUDA(cudaEventRecord(s->comm_ev[0], 0));
+        VRT_CUDA(cudaStreamWaitEvent(cs, s->comm_ev[0], 0));
+        VRT_TRY(comm_op(s->comm, buf, count, op, cs));
+        VRT_CUDA(cudaEventRecord(s->comm_ev[1], cs));
+        VRT_CUDA(cudaStreamWaitEvent(0, s->comm_ev[1], 0));
+        return VRT_OK;
+    }
+    if (s->allreduce) {
+        VRT_CUDA(cudaDeviceSynchronize());
+        int rc = s->allreduce(buf, count, op, s->allreduce_user);
+        if (rc != 0) {
+            set_error("exchange hook failed (%d) in op %d", rc, op);
+            return VRT_E_STATE;
+        }
+    }
+    return VRT_OK;
+}
+
 // J_λ_voronoi on device state: s->S -> s->J (internal order)
 // scatter: false = all-reduce J over the direction shards (every rank gets the full J); true = reduce-scatter over cells
 static int mean_intensity_internal(vrt_solver* s, SweepStats* stats, double* t_opacity_ms, double* t_sweep_ms, bool scatter = false) {
@@ -833,14 +867,10 @@ static int mean_intensity_internal(vrt_solver* s, SweepStats* stats, double* t_o
         opacity_ms += ms;
     }
     if (s->nd == 0) VRT_CUDA(cudaMemset(s->J.p, 0, sizeof(double) * (size_t)n * s->nlam));   // no direction: J = 0, whatever J held
-    if (s->dir_sharded && s->allreduce) {
+    if (s->dir_sharded && s->has_exchange()) {
         // J = sum over the direction shards (lambda_iteration.jl:102,107 add the directions one after the other)
-        int rc = scatter ? s->allreduce(s->J.p, s->n_pad * s->nlam, 3, s->allreduce_user)
-                         : s->allreduce(s->J.p, n * s->nlam, 2, s->allreduce_user);
-        if (rc != 0) {
-            set_error("all-reduce hook failed (%d)", rc);
-            return VRT_E_STATE;
-        }
+        if (scatter) VRT_TRY(exchange(s, s->J.p, s->n_pad * s->nlam, 3));
+        else VRT_TRY(exchange(s, s->J.p, n * s->nlam, 2));
     }
     if (t_opacity_ms) *t_opacity_ms = opacity_ms;
     if (t_sweep_ms) *t_sweep_ms = stats->sweep_ms;
@@ -866,14 +896,7 @@ static int rates_internal(vrt_solver* s, const double* damping_int, int64_t c0, 
                                      damping_int ? damping_int + c0 * s->nlam : nullptr, s->lte.p + c0, s->J.p + c0 * s->nlam, s->Rp.p + c0);
     }
     VRT_CUDA(cudaGetLastError());
-    if (s->allreduce) {
-        VRT_CUDA(cudaDeviceSynchronize());
-        int rc = s->allreduce(s->Rp.p, 6 * n, 0, s->allreduce_user);
-        if (rc != 0) {
-            set_error("all-reduce hook failed (%d)", rc);
-            return VRT_E_STATE;
-        }
-    }
+    if (s->has_exchange()) VRT_TRY(exchange(s, s->Rp.p, 6 * n, 0));
     return VRT_OK;
 }
 
@@ -884,18 +907,13 @@ static int read_diff(vrt_solver* s, double* diff) {
     VRT_CUDA(cudaMemcpy(&isn, s->diff_nan.p, sizeof(isn), cudaMemcpyDeviceToHost));
     double d;
     memcpy(&d, &bits, sizeof(d));
-    if (s->allreduce) {
-        // max over shards; NaN is carried as +inf-like flag through a second reduction
-        DevBuf<double> tmp;
-        VRT_TRY(tmp.alloc(2));
+    if (s->has_exchange()) {
+        // max over shards; NaN is carried as a flag through the same reduction
+        VRT_TRY(s->diff_pair.ensure(2));
         double h[2] = {d, isn ? 1.0 : 0.0};
-        VRT_CUDA(cudaMemcpy(tmp.p, h, sizeof(h), cudaMemcpyHostToDevice));
-        int rc = s->allreduce(tmp.p, 2, 1, s->allreduce_user);
-        if (rc != 0) {
-            set_error("all-reduce hook failed (%d)", rc);
-            return VRT_E_STATE;
-        }
-        VRT_CUDA(cudaMemcpy(h, tmp.p, sizeof(h), cudaMemcpyDeviceToHost));
+        VRT_CUDA(cudaMemcpy(s->diff_pair.p, h, sizeof(h), cudaMemcpyHostToDevice));
+        VRT_TRY(exchange(s, s->diff_pair.p, 2, 1));
+        VRT_CUDA(cudaMemcpy(h, s->diff_pair.p, sizeof(h), cudaMemcpyDeviceToHost));
         d = h[0];
         isn = h[1] != 0.0;
     }
@@ -1286,7 +1304,7 @@ int vrt_lambda_iterate(vrt_solver* s, double eps, int32_t maxiter, vrt_iter_cb c
     int i = 0;
     SweepStats total;
     // post-J stages on this rank's cell slice only (reduce-scatter of J, all-gather of S and populations)
-    const bool cshard = s->cell_R > 1 && s->dir_sharded && s->allreduce && s->is_line;
+    const bool cshard = s->cell_R > 1 && s->dir_sharded && s->has_exchange() && s->is_line;
     const int64_t c0 = cshard ? s->c0 : 0, c1 = cshard ? s->c1 : n, cn = c1 - c0;
     while (diff > eps && i < maxiter) {
         auto t0 = std::chrono::steady_clock::now();
@@ -1318,13 +1336,8 @@ int vrt_lambda_iterate(vrt_solver* s, double eps, int32_t maxiter, vrt_iter_cb c
             VRT_TRY(s->pops_blk.ensure((size_t)3 * s->n_pad));
             k_pack_pops<<<nblocks(s->cs, 256), 256>>>(n, s->cs * s->cell_r, s->cs, s->pops.p, s->pops_blk.p + (size_t)3 * s->cs * s->cell_r);
             VRT_CUDA(cudaGetLastError());
-            VRT_CUDA(cudaDeviceSynchronize());
-            int rc = s->allreduce(s->pops_blk.p, 3 * s->n_pad, 4, s->allreduce_user);
-            if (rc == 0) rc = s->allreduce(s->S.p, s->n_pad * s->nlam, 4, s->allreduce_user);
-            if (rc != 0) {
-                set_error("all-gather hook failed (%d)", rc);
-                return VRT_E_STATE;
-            }
+            VRT_TRY(exchange(s, s->pops_blk.p, 3 * s->n_pad, 4));
+            VRT_TRY(exchange(s, s->S.p, s->n_pad * s->nlam, 4));
             k_unpack_pops<<<nblocks(n, 256), 256>>>(n, s->cs, s->cell_R, s->pops_blk.p, s->pops.p);
             stats.kernels += 2;
         }
@@ -1363,13 +1376,8 @@ int vrt_get_state(vrt_solver* s, double* S, double* J, double* populations) {
     const int64_t n = s->n;
     if (S) VRT_TRY(download_rows(s->g, s->S.p, S, s->nlam, s->stage));
     if (J) {
-        if (s->cell_R > 1 && s->dir_sharded && s->allreduce && s->is_line) {   // J lives as cell slices: gather it (collective call)
-            int rc = s->allreduce(s->J.p, s->n_pad * s->nlam, 4, s->allreduce_user);
-            if (rc != 0) {
-                set_error("all-gather hook failed (%d)", rc);
-                return VRT_E_STATE;
-            }
-        }
+        if (s->cell_R > 1 && s->dir_sharded && s->has_exchange() && s->is_line)   // J lives as cell slices: gather it (collective call)
+            VRT_TRY(exchange(s, s->J.p, s->n_pad * s->nlam, 4));
         VRT_TRY(download_rows(s->g, s->J.p, J, s->nlam, s->stage));
     }
     if (populations && s->is_line) {
@@ -1379,6 +1387,117 @@ int vrt_get_state(vrt_solver* s, double* S, double* J, double* populations) {
         k_scatter_cols<<<nblocks(n, 256), 256>>>(s->pops.p, o, s->g->site_of.p, n, 3);
         VRT_CUDA(cudaGetLastError());
         if (o != populations) VRT_TRY(copy_out(populations, o, sizeof(double) * 3 * n));
+    }
+    VRT_CUDA(cudaDeviceSynchronize());
+    return VRT_OK;
+}
+
+struct AbsOp {
+    __host__ __device__ double operator()(const double& x) const { return fabs(x); }
+};
+
+int vrt_state_checksum(vrt_solver* s, double out[4]) {
+    if (!s || !out) return VRT_E_INVALID;
+    VRT_TRY(ensure_state(s));
+    const int64_t n = s->n;
+    const int64_t ns = n * s->nlam;
+    if (ns >= (int64_t)INT32_MAX * 8) {
+        set_error("vrt_state_checksum: state too large");
+        return VRT_E_INVALID;
+    }
+    DevBuf<double> res;
+    DevBuf<char> tmp;
+    VRT_TRY(res.alloc(4));
+    VRT_CUDA(cudaMemset(res.p, 0, 4 * sizeof(double)));
+    cub::TransformInputIterator<double, AbsOp, const double*> absS(s->S.p, AbsOp());
+    size_t b0 = 0, b1 = 0;
+    VRT_CUDA(cub::DeviceReduce::Sum(nullptr, b0, s->S.p, res.p, ns));
+    VRT_CUDA(cub::DeviceReduce::Max(nullptr, b1, absS, res.p + 1, ns));
+    VRT_TRY(tmp.alloc(std::max(b0, b1)));
+    size_t b = tmp.n;
+    VRT_CUDA(cub::DeviceReduce::Sum(tmp.p, b, s->S.p, res.p, ns));
+    b = tmp.n;
+    VRT_CUDA(cub::DeviceReduce::Max(tmp.p, b, absS, res.p + 1, ns));
+    if (s->is_line) {
+        b = tmp.n;
+        VRT_CUDA(cub::DeviceReduce::Sum(tmp.p, b, s->pops.p, res.p + 2, 3 * n));
+    }
+    // J lives as cell slices when the post-J stages are cell-sharded: sum of this rank's slice only
+    const bool cshard = s->cell_R > 1 && s->dir_sharded && s->has_exchange() && s->is_line;
+    const int64_t c0 = cshard ? s->c0 : 0, c1 = cshard ? s->c1 : n;
+    b = tmp.n;
+    if (c1 > c0) VRT_CUDA(cub::DeviceReduce::Sum(tmp.p, b, s->J.p + c0 * s->nlam, res.p + 3, (c1 - c0) * s->nlam));
+    VRT_CUDA(cudaMemcpy(out, res.p, 4 * sizeof(double), cudaMemcpyDeviceToHost));
+    return VRT_OK;
+}
+
+int vrt_solver_comm_init(vrt_solver* s, const char* dir_id, int32_t dir_rank, int32_t dir_size, const char* lam_id, int32_t lam_rank,
+                         int32_t lam_size) {
+    if (!s) return VRT_E_INVALID;
+    if (s->cell_R > 1 && dir_size != s->cell_R) {
+        set_error("vrt_solver_comm_init: the direction group has %d processes but the solver was created with %d cell shards", dir_size, s->cell_R);
+        return VRT_E_INVALID;
+    }
+    if (s->cell_R > 1 && dir_rank != s->cell_r) {
+        set_error("vrt_solver_comm_init: rank %d in the direction group but cell shard %d", dir_rank, s->cell_r);
+        return VRT_E_INVALID;
+    }
+    if (s->comm) {
+        comm_free(s->comm);
+        s->comm = nullptr;
+    }
+    return comm_create(dir_id, dir_rank, dir_size, lam_id, lam_rank, lam_size, &s->comm);
+}
+
+int vrt_solver_cell_slice(const vrt_solver* s, int64_t* first, int64_t* last) {
+    if (!s || !first || !last) return VRT_E_INVALID;
+    const bool cshard = s->cell_R > 1 && s->dir_sharded && s->is_line;
+    *first = cshard ? s->c0 : 0;
+    *last = cshard ? s->c1 : s->n;
+    return VRT_OK;
+}
+
+// own cell slice, internal order: S, J rows [c0, c1) are contiguous, the populations are three runs of the SoA arrays
+int vrt_get_state_slice(vrt_solver* s, double* S, double* J, double* populations) {
+    if (!s) return VRT_E_INVALID;
+    VRT_TRY(ensure_state(s));
+    int64_t c0 = 0, c1 = 0;
+    VRT_TRY(vrt_solver_cell_slice(s, &c0, &c1));
+    const int64_t cn = c1 - c0, n = s->n;
+    if (S) VRT_TRY(copy_out(S, s->S.p + c0 * s->nlam, sizeof(double) * (size_t)cn * s->nlam));
+    if (J) VRT_TRY(copy_out(J, s->J.p + c0 * s->nlam, sizeof(double) * (size_t)cn * s->nlam));
+    if (populations && s->is_line)
+        for (int k = 0; k < 3; k++) VRT_TRY(copy_out(populations + (size_t)k * cn, s->pops.p + (size_t)k * n + c0, sizeof(double) * (size_t)cn));
+    VRT_CUDA(cudaDeviceSynchronize());
+    return VRT_OK;
+}
+
+int vrt_set_state_slice(vrt_solver* s, const double* S, const double* populations) {
+    if (!s) return VRT_E_INVALID;
+    VRT_TRY(ensure_state(s));
+    int64_t c0 = 0, c1 = 0;
+    VRT_TRY(vrt_solver_cell_slice(s, &c0, &c1));
+    const int64_t cn = c1 - c0, n = s->n;
+    const bool cshard = cn < n;
+    if (cshard && !s->has_exchange()) {
+        set_error("vrt_set_state_slice: cell-sharded solver without collectives (vrt_solver_comm_init / vrt_solver_set_allreduce)");
+        return VRT_E_STATE;
+    }
+    if (S) {
+        VRT_TRY(copy_in(s->S.p + c0 * s->nlam, S, sizeof(double) * (size_t)cn * s->nlam));
+        // the other processes' slices come over NVLink, not over every process's PCIe link
+        if (cshard) VRT_TRY(exchange(s, s->S.p, s->n_pad * s->nlam, 4));
+    }
+    if (populations && s->is_line) {
+        for (int k = 0; k < 3; k++) VRT_TRY(copy_in(s->pops.p + (size_t)k * n + c0, populations + (size_t)k * cn, sizeof(double) * (size_t)cn));
+        if (cshard) {
+            VRT_TRY(s->pops_blk.ensure((size_t)3 * s->n_pad));
+            k_pack_pops<<<nblocks(s->cs, 256), 256>>>(n, s->cs * s->cell_r, s->cs, s->pops.p, s->pops_blk.p + (size_t)3 * s->cs * s->cell_r);
+            VRT_CUDA(cudaGetLastError());
+            VRT_TRY(exchange(s, s->pops_blk.p, 3 * s->n_pad, 4));
+            k_unpack_pops<<<nblocks(n, 256), 256>>>(n, s->cs, s->cell_R, s->pops_blk.p, s->pops.p);
+            VRT_CUDA(cudaGetLastError());
+        }
     }
     VRT_CUDA(cudaDeviceSynchronize());
     return VRT_OK;

@@ -48,29 +48,50 @@ struct SweepParams {
     unsigned long long* prof; // experiment 2: per-role cycle counters
 };
 
-// exp(x) for the sweep: Cody–Waite reduction x = k ln2 + r, |r| <= ln2/2, degree-13 Taylor polynomial (truncation
-// 4e-18), scaling by 2^k through the exponent field.  ~20 instructions, no fp64<->int conversion, no special-case
-// branches; relative error <= ~2 ulp for -700 <= x <= 700 (outside, the argument is clamped: linear_weights never
-// uses e for Δτ > 50).
+// Constants of the sweep's exp, kept in the constant bank so that every DFMA takes its coefficient as a c[bank][offset]
+// operand (as immediates they cost two extra issue slots each: the polynomial was 26 of 74 instructions UMOV/MOV).
+__constant__ double EXP_C[18] = {
+    1.4426950408889634074,        // 0  log2(e)
+    6755399441055744.0,           // 1  1.5 * 2^52: rounds to nearest integer
+    -6.93147180369123816490e-01,  // 2  -ln2 high part (fdlibm split)
+    -1.90821492927058770002e-10,  // 3  -ln2 low part
+    1.6059043836821614599e-10,    // 4  1/13!
+    2.0876756987868098979e-09,    // 5  1/12!
+    2.5052108385441718775e-08,    // 6  1/11!
+    2.7557319223985890653e-07,    // 7  1/10!
+    2.7557319223985892511e-06,    // 8  1/9!
+    2.4801587301587301566e-05,    // 9  1/8!
+    1.9841269841269841253e-04,    // 10 1/7!
+    1.3888888888888889419e-03,    // 11 1/6!
+    8.3333333333333332177e-03,    // 12 1/5!
+    4.1666666666666664354e-02,    // 13 1/4!
+    1.6666666666666665741e-01,    // 14 1/3!
+    -708.0,                       // 15 lower clamp of the argument (exp(-708) = 3e-308 is still a normal number)
+    3.3333333333333331483e-01,    // 16 1/3
+    1.6666666666666665741e-01,    // 17 1/6
+};
+
+// exp(x) for x <= 0: Cody–Waite reduction x = k ln2 + r, |r| <= ln2/2, degree-13 Taylor polynomial (truncation
+// 4e-18), scaling by 2^k through the exponent field.  No fp64<->int conversion, no special-case branches;
+// relative error <= ~2 ulp for -708 <= x <= 0 (below, the argument is clamped: linear_weights never uses e for Δτ > 50).
 __device__ __forceinline__ double exp_sweep(double x) {
-    x = fmin(fmax(x, -700.0), 700.0);
-    const double MAGIC = 6755399441055744.0;                   // 1.5 * 2^52: rounds to nearest integer
-    const double t = fma(x, 1.4426950408889634074, MAGIC);
-    const double kf = t - MAGIC;
+    x = x < EXP_C[15] ? EXP_C[15] : x;   // (not fmax: its NaN handling costs five more instructions)
+    const double t = fma(x, EXP_C[0], EXP_C[1]);
+    const double kf = t - EXP_C[1];
     const int k = __double2loint(t);
-    double r = fma(kf, -6.93147180369123816490e-01, x);        // ln2 high part (fdlibm split)
-    r = fma(kf, -1.90821492927058770002e-10, r);               // ln2 low part
-    double p = 1.6059043836821614599e-10;                      // 1/13!
-    p = fma(p, r, 2.0876756987868098979e-09);                  // 1/12!
-    p = fma(p, r, 2.5052108385441718775e-08);                  // 1/11!
-    p = fma(p, r, 2.7557319223985890653e-07);                  // 1/10!
-    p = fma(p, r, 2.7557319223985892511e-06);                  // 1/9!
-    p = fma(p, r, 2.4801587301587301566e-05);                  // 1/8!
-    p = fma(p, r, 1.9841269841269841253e-04);                  // 1/7!
-    p = fma(p, r, 1.3888888888888889419e-03);                  // 1/6!
-    p = fma(p, r, 8.3333333333333332177e-03);                  // 1/5!
-    p = fma(p, r, 4.1666666666666664354e-02);                  // 1/4!
-    p = fma(p, r, 1.6666666666666665741e-01);                  // 1/3!
+    double r = fma(kf, EXP_C[2], x);
+    r = fma(kf, EXP_C[3], r);
+    double p = EXP_C[4];
+    p = fma(p, r, EXP_C[5]);
+    p = fma(p, r, EXP_C[6]);
+    p = fma(p, r, EXP_C[7]);
+    p = fma(p, r, EXP_C[8]);
+    p = fma(p, r, EXP_C[9]);
+    p = fma(p, r, EXP_C[10]);
+    p = fma(p, r, EXP_C[11]);
+    p = fma(p, r, EXP_C[12]);
+    p = fma(p, r, EXP_C[13]);
+    p = fma(p, r, EXP_C[14]);
     p = fma(p, r, 0.5);
     p = fma(p, r, 1.0);
     p = fma(p, r, 1.0);
@@ -88,16 +109,21 @@ __device__ __forceinline__ double rcp_sweep(double a) {
     return y;
 }
 
-// linear_weights (functions.jl:484-500), branch-free: the three branches are evaluated with selects so that a
-// warp whose lanes hold different wavelengths (very different Δτ) does not serialise them.
+// linear_weights (functions.jl:484-500), branch-free: a warp's lanes hold different wavelengths (line core: large Δτ, far
+// wing and corona: Δτ < 5e-4), so branches would serialise.  The three cases are folded as follows:
+//   Δτ > 50:  the reference sets e = 0, a = 1/Δτ, b = 1 - a.  The general expressions give exactly these a and b there
+//             (exp(-Δτ) < 2e-22 is below half an ulp of 1, of 1/Δτ and of 1 - 1/Δτ), so only e needs a select;
+//   Δτ < 5e-4: Taylor forms (the two divisions by 3 and 6 as multiplications: x/3 and x*(1/3) differ by at most an ulp of a
+//             term that is < 2e-4 of the 0.5 it is subtracted from).
 __device__ __forceinline__ void linear_weights(double dtau, double& a, double& b, double& e) {
     const double ex = exp_sweep(-dtau);
     const double inv = rcp_sweep(dtau);
     const double a_mid = (1 - ex) * inv - ex;
-    const bool small = dtau < 5e-4, large = dtau > 50;
-    e = small ? (1 - dtau + 0.5 * (dtau * dtau)) : (large ? 0.0 : ex);
-    a = small ? dtau * (1.0 / 2 - dtau / 3) : (large ? inv : a_mid);
-    b = small ? dtau * (1.0 / 2 - dtau / 6) : (large ? 1.0 - inv : 1 - a_mid - ex);
+    const double b_mid = 1 - a_mid - ex;
+    const bool small = dtau < 5e-4;
+    e = small ? (1 - dtau + 0.5 * (dtau * dtau)) : (dtau > 50 ? 0.0 : ex);
+    a = small ? dtau * (0.5 - dtau * EXP_C[16]) : a_mid;
+    b = small ? dtau * (0.5 - dtau * EXP_C[17]) : b_mid;
 }
 
 __device__ __forceinline__ double load_I(uint32_t src, const DirDev* __restrict__ D, int nlam, int l) {
@@ -477,27 +503,31 @@ __global__ void __launch_bounds__(32 * (TMA_NP + TMA_NC), 3) k_sweep_tma(const S
             const StageHdr h = hdr[stage];
             if (!h.valid) break;
             if (P.experiment == 2) k1 = clock64();
+            // rows of the stage, already shifted by the row's alignment offset and by this lane's first wavelength: inside
+            // the wavelength loop every operand is then one LDS with an immediate offset
             const unsigned char* rb = data + (size_t)stage * 8 * rowb;
-            const double* r0 = reinterpret_cast<const double*>(rb) + (h.offs & 1u);
-            const double* r1 = reinterpret_cast<const double*>(rb + rowb) + ((h.offs >> 1) & 1u);
-            const double* r2 = reinterpret_cast<const double*>(rb + 2 * rowb) + ((h.offs >> 2) & 1u);
-            const double* r3 = reinterpret_cast<const double*>(rb + 3 * rowb) + ((h.offs >> 3) & 1u);
-            const double* r4 = reinterpret_cast<const double*>(rb + 4 * rowb) + ((h.offs >> 4) & 1u);
-            const double* r5 = reinterpret_cast<const double*>(rb + 5 * rowb) + ((h.offs >> 5) & 1u);
-            const double* r6 = reinterpret_cast<const double*>(rb + 6 * rowb) + ((h.offs >> 6) & 1u);
-            const double* r7 = reinterpret_cast<const double*>(rb + 7 * rowb) + ((h.offs >> 7) & 1u);
+            const double* r0 = reinterpret_cast<const double*>(rb) + (h.offs & 1u) + lane;
+            const double* r1 = reinterpret_cast<const double*>(rb + rowb) + ((h.offs >> 1) & 1u) + lane;
+            const double* r2 = reinterpret_cast<const double*>(rb + 2 * rowb) + ((h.offs >> 2) & 1u) + lane;
+            const double* r3 = reinterpret_cast<const double*>(rb + 3 * rowb) + ((h.offs >> 3) & 1u) + lane;
+            const double* r4 = reinterpret_cast<const double*>(rb + 4 * rowb) + ((h.offs >> 4) & 1u) + lane;
+            const double* r5 = reinterpret_cast<const double*>(rb + 5 * rowb) + ((h.offs >> 5) & 1u) + lane;
+            const double* r6 = reinterpret_cast<const double*>(rb + 6 * rowb) + ((h.offs >> 6) & 1u) + lane;
+            const double* r7 = reinterpret_cast<const double*>(rb + 7 * rowb) + ((h.offs >> 7) & 1u) + lane;
+            double* out = h.dst + lane;
             const bool z1 = (h.offs >> 12) & 1u, z2 = (h.offs >> 15) & 1u;
-            for (int l = lane; l < nlam; l += 32) {
-                const double a_c = r0[l], S_c = r1[l];
-                const double I_1 = z1 ? 0.0 : r4[l];
-                const double I_2 = z2 ? 0.0 : r7[l];
+            auto item = [&](int o) {
+                const double a_c = r0[o], S_c = r1[o];
+                const double I_1 = z1 ? 0.0 : r4[o];
+                const double I_2 = z2 ? 0.0 : r7[o];
                 double a, b, e;
-                linear_weights(h.hr1 * (a_c + r2[l]), a, b, e);
-                double I = 0.0 + (e * I_1 + a * r3[l] + b * S_c) * h.w1;
-                linear_weights(h.hr2 * (a_c + r5[l]), a, b, e);
-                I += (e * I_2 + a * r6[l] + b * S_c) * h.w2;
-                h.dst[l] = I;
-            }
+                linear_weights(h.hr1 * (a_c + r2[o]), a, b, e);
+                double I = 0.0 + (e * I_1 + a * r3[o] + b * S_c) * h.w1;
+                linear_weights(h.hr2 * (a_c + r5[o]), a, b, e);
+                I += (e * I_2 + a * r6[o] + b * S_c) * h.w2;
+                out[o] = I;
+            };
+            for (int o = 0; lane + o < nlam; o += 32) item(o);
             __syncwarp();   // every lane has read its part of the stage and issued its stores
             if (lane == 0) {
                 __threadfence_block();   // release: the warp's reads of the stage are ordered before the hand-back

@@ -204,6 +204,12 @@ int sweep_collect(vrt_grid* g, SweepStats* stats);
 void sweep_timers_free(void* p);
 int sweep_scratch_rows(const DirSchedule* sch, int s);
 
+// comm.cu: in-library NCCL communicators of a solver and the exchange steps of the Λ-iteration
+int comm_create(const char* dir_id, int dir_rank, int dir_size, const char* lam_id, int lam_rank, int lam_size, void** out);
+void comm_free(void* comm);
+cudaStream_t comm_stream(void* comm);
+int comm_op(void* comm, double* buf, int64_t count, int op, cudaStream_t st);
+
 // misc kernels (physics.cu)
 int permute_rows(const double* src, double* dst, const int32_t* map, int64_t n, int64_t nlam, int gather, cudaStream_t st);
 extern thread_local SweepStats g_last_stats;

@@ -79,12 +79,79 @@ def sample_sites(n, seed=2022, stratified=True):
     return out
 
 
-def voronoi_neighbours(positions, bounds=None, voro_exec=None, workdir=None, keep=False):
-    """write_arrays + voro + the parsing half of read_cell -> NeighbourMatrix (n, ld)."""
+FIELDS = ("temperature", "electron_density", "hydrogen_density", "velocity_z", "velocity_x", "velocity_y")
+
+
+def cube_atmosphere(nz=216, nx=129, ny=129, seed=2022):
+    """The synthetic atmosphere on a regular cube spanning BOX (what the reference reads from its Bifrost HDF5 file,
+    src/io.jl get_atmos): -> (api.Atmosphere, quantity) with quantity = log10(N_H)^-2 T^-2/5, the density the reference
+    samples its sites from (src/sample_grids.jl:223-230)."""
+    z = np.linspace(BOX["z_min"], BOX["z_max"], nz)
+    x = np.linspace(BOX["x_min"], BOX["x_max"], nx)
+    y = np.linspace(BOX["y_min"], BOX["y_max"], ny)
+    Z, X, Y = np.meshgrid(z, x, y, indexing="ij")
+    a = atmosphere(Z.ravel(), X.ravel(), Y.ravel(), seed)
+    f = {k: np.asfortranarray(a[k].reshape(nz, nx, ny)) for k in FIELDS}
+    atm = api.Atmosphere(z, x, y, f["temperature"], f["electron_density"], f["hydrogen_density"], f["velocity_z"], f["velocity_x"],
+                         f["velocity_y"])
+    q = np.asfortranarray(np.log10(f["hydrogen_density"]) ** -2.0 * f["temperature"] ** (-2.0 / 5.0))
+    return atm, q
+
+
+def native_sites(n, seed=2022, cube=None):
+    """The reference's set-up pipeline on the GPU (compare_line.jl:49-110 without voro++): rejection sampling of n sites
+    from the cube (functions.jl:79-121 -> vrt_rejection_sampling) and trilinear initialisation of the six per-site fields
+    (voronoi_utils.jl:687-708 -> vrt_trilinear).  -> positions (3, n), dict of per-site fields"""
+    atm, q = cube or cube_atmosphere(seed=seed)
+    pos = api.rejection_sampling(n, atm, q, seed)
+    vals = api.initialise(pos, atm)
+    return pos, dict(zip(FIELDS, vals))
+
+
+def _trilinear_np(atm, vals, pos):
+    """numpy restatement of functions.jl:207-248 on the uniform cube of cube_atmosphere (CPU arm of bench.py only)"""
+    def cell(ax, p):
+        i = np.clip(((p - ax[0]) / (ax[1] - ax[0])).astype(np.int64), 0, len(ax) - 2)
+        return i, (p - ax[i]) / (ax[i + 1] - ax[i])
+    iz, tz = cell(atm.z, pos[0])
+    ix, tx = cell(atm.x, pos[1])
+    iy, ty = cell(atm.y, pos[2])
+    out = 0.0
+    for dz, wz in ((0, 1 - tz), (1, tz)):
+        for dx, wx in ((0, 1 - tx), (1, tx)):
+            for dy, wy in ((0, 1 - ty), (1, ty)):
+                out = out + wz * wx * wy * vals[iz + dz, ix + dx, iy + dy]
+    return out
+
+
+def native_sites_cpu(n, seed=2022, cube=None):
+    """the same pipeline in numpy (same cube, same acceptance rule, numpy's random stream): the sites of the CPU baseline arm"""
+    atm, q = cube or cube_atmosphere(seed=seed)
+    rng = np.random.default_rng(seed)
+    lo = np.array([atm.z[0], atm.x[0], atm.y[0]])
+    hi = np.array([atm.z[-1], atm.x[-1], atm.y[-1]])
+    qmin, qmax = q.min(), q.max()
+    out = np.empty((3, n), order="F")
+    got = 0
+    while got < n:
+        m = max(4 * (n - got), 100000)
+        cand = lo[:, None] + (hi - lo)[:, None] * rng.random((3, m))
+        keep = _trilinear_np(atm, q, cand) > rng.uniform(qmin, qmax, size=m)
+        sel = cand[:, keep][:, : n - got]
+        out[:, got:got + sel.shape[1]] = sel
+        got += sel.shape[1]
+    fields = (atm.temperature, atm.electron_density, atm.hydrogen_populations, atm.velocity_z, atm.velocity_x, atm.velocity_y)
+    return out, {k: _trilinear_np(atm, f, out) for k, f in zip(FIELDS, fields)}
+
+
+def voronoi_neighbours(positions, bounds=None, voro_exec=None, workdir=None, keep=False, parse=None):
+    """write_arrays + voro + the parsing half of read_cell -> NeighbourMatrix (n, ld).
+    parse(fname, n) -> (n, ld) matrix replaces api.read_neighbours (the CPU baseline arm of bench.py parses with the
+    oracle so that its process never loads libvrt.so)."""
     b = bounds or BOX
     voro_exec = voro_exec or api.default_voro_exec()
     if voro_exec is None:
-        raise FileNotFoundError("voro++ driver not found (VORO_EXEC, /root/reference/rt_preprocessing/output_sites, oracle/_ref/output_sites)")
+        raise FileNotFoundError("voro++ driver not found (VORO_EXEC, /root/reference/rt_preprocessing/output_sites, baseline/_ref/output_sites)")
     n = positions.shape[1]
     tmp = workdir or tempfile.mkdtemp(prefix="vrt_voro_")
     sites_file = os.path.join(tmp, "sites.txt")
@@ -93,7 +160,7 @@ def voronoi_neighbours(positions, bounds=None, voro_exec=None, workdir=None, kee
     ids = np.arange(1, n + 1)
     np.savetxt(sites_file, np.column_stack([ids, positions[1], positions[2], positions[0]]), fmt=["%d", "%.17g", "%.17g", "%.17g"], delimiter="\t")
     api.voro(voro_exec, sites_file, nb_file, b["x_min"], b["x_max"], b["y_min"], b["y_max"], b["z_min"], b["z_max"])
-    nbr = api.read_neighbours(nb_file, n)
+    nbr = (parse or api.read_neighbours)(nb_file, n)
     if not keep and workdir is None:
         for f in (sites_file, nb_file):
             os.remove(f)
