@@ -46,6 +46,7 @@ enum {
 
 typedef struct vrt_grid vrt_grid;       /* replaces VoronoiSites' grid part (voronoi_utils.jl:7-28)   */
 typedef struct vrt_solver vrt_solver;   /* state of Λ_voronoi (lambda_iteration.jl:207, lambda_continuum.jl:109) */
+typedef struct vrt_outfile vrt_outfile; /* the HDF5 output / checkpoint file of create_output_file (io.jl:159-225)          */
 
 /* Two-level + continuum hydrogenic atom: the scalar fields of HydrogenicLine (line.jl:14-72) plus the
  * three broadening constants γ_constant evaluates once per call (broadening.jl:63-82).
@@ -338,6 +339,27 @@ int vrt_set_state(vrt_solver* s, const double* S, const double* populations);
 int vrt_solver_cell_slice(const vrt_solver* s, int64_t* first, int64_t* last);
 int vrt_get_state_slice(vrt_solver* s, double* S, double* J, double* populations);
 int vrt_set_state_slice(vrt_solver* s, const double* S, const double* populations);
+
+/* ---------------------------------------------------------------- output / checkpoint file
+ * create_output_file + write_to_file (io.jl:57-225) without the HDF5 library: a version-0-superblock HDF5 file with one flat
+ * root group of contiguous little-endian datasets carrying the reference's names and shapes, so that
+ * recover_simulation.jl:213-277 and python/*.py read it like a file written by HDF5.jl.  Dataset names (Voronoi,
+ * io.jl:196-225): source_function (nλ, n_sites), populations (n_sites, 3), positions (3, n_sites), temperature,
+ * hydrogen_populations, electron_density, velocity_z, velocity_x, velocity_y (n_sites), boundaries (6), convergence
+ * (maxiter+1, created as zeros), n_bb, n_bf (1, Int64), wavelength (nλ), line_center (1), time (1); the regular-grid form
+ * (io.jl:159-190) has z, x, y and (nz, nx, ny)-shaped fields instead.  Shapes are Julia shapes: the file stores them with the
+ * dimensions reversed over the same bytes, as HDF5.jl does.  All values Float64 unless noted. */
+int vrt_output_create(const char* path, int64_t nlam, int64_t n_sites, int64_t maxiter, vrt_outfile** out);
+int vrt_output_create_regular(const char* path, int64_t nlam, int64_t nz, int64_t nx, int64_t ny, int64_t maxiter, vrt_outfile** out);
+int vrt_output_dataset_size(const vrt_outfile* f, const char* name, int64_t* nbytes);
+/* write_to_file(array, output_path): the whole dataset; data is a host or device pointer of exactly the dataset's size */
+int vrt_output_write(vrt_outfile* f, const char* name, const void* data, int64_t nbytes);
+/* write_to_file(difference, iteration, output_path) (io.jl:129-135): convergence[iteration] = difference, 1-based */
+int vrt_output_write_convergence(vrt_outfile* f, int64_t iteration, double difference);
+/* write_to_file(S_λ, …) and write_to_file(populations, …) straight from the solver's device state (what Λ_voronoi does after
+ * every iteration, lambda_iteration.jl:280-281); call it from the vrt_iter_cb of vrt_lambda_iterate */
+int vrt_output_write_state(vrt_outfile* f, vrt_solver* s);
+int vrt_output_close(vrt_outfile* f);
 
 /* Fingerprint of the device-resident state, reduced on the device (nothing the size of S crosses the bus):
  * out[0] = Σ S, out[1] = max |S|, out[2] = Σ populations (0 for the continuum solver), out[3] = Σ J over the cells this

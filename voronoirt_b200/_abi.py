@@ -111,6 +111,13 @@ PROTOTYPES = {
     "vrt_get_state": (C.c_int, [C.c_void_p, P, P, P]),
     "vrt_set_state": (C.c_int, [C.c_void_p, P, P]),
     "vrt_state_checksum": (C.c_int, [C.c_void_p, c_double_p]),
+    "vrt_output_create": (C.c_int, [C.c_char_p, C.c_int64, C.c_int64, C.c_int64, C.POINTER(C.c_void_p)]),
+    "vrt_output_create_regular": (C.c_int, [C.c_char_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.POINTER(C.c_void_p)]),
+    "vrt_output_dataset_size": (C.c_int, [C.c_void_p, C.c_char_p, c_int64_p]),
+    "vrt_output_write": (C.c_int, [C.c_void_p, C.c_char_p, P, C.c_int64]),
+    "vrt_output_write_convergence": (C.c_int, [C.c_void_p, C.c_int64, C.c_double]),
+    "vrt_output_write_state": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "vrt_output_close": (C.c_int, [C.c_void_p]),
     "vrt_nccl_available": (C.c_int, []),
     "vrt_nccl_version": (C.c_int, [c_int32_p]),
     "vrt_nccl_unique_id": (C.c_int, [C.c_char_p]),

@@ -305,6 +305,69 @@ class VoronoiSites:
         self._grid = g
 
 
+# ------------------------------------------------------------------ io.jl: output / checkpoint file
+class OutputFile:
+    """vrt_outfile handle: the HDF5 file of create_output_file (src/io.jl:159-225), written without the HDF5 library"""
+
+    def __init__(self, h, path):
+        self.h, self.path = h, path
+
+    def write(self, name, array):
+        """write_to_file for any dataset: `array` is a numpy array (Julia shape, column-major) or a torch CUDA tensor"""
+        a = array if hasattr(array, "data_ptr") else (np.asfortranarray(array, dtype=np.int64) if name in ("n_bb", "n_bf") else _f(array))
+        nbytes = a.numel() * a.element_size() if hasattr(a, "data_ptr") else a.nbytes
+        check(lib().vrt_output_write(self.h, name.encode(), _ptr(a), int(nbytes)))
+
+    def write_convergence(self, iteration, difference):
+        check(lib().vrt_output_write_convergence(self.h, int(iteration), float(difference)))
+
+    def write_state(self, solver):
+        """source_function and populations straight from the solver's device state (lambda_iteration.jl:280-281)"""
+        check(lib().vrt_output_write_state(self.h, solver.h))
+
+    def close(self):
+        if self.h:
+            h, self.h = self.h, None
+            check(lib().vrt_output_close(h))
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+
+def create_output_file(output_path, nλ, size, maxiter):
+    """src/io.jl:159-225: size = n_sites (Voronoi) or (nz, nx, ny) (regular grid) -> OutputFile"""
+    h = C.c_void_p()
+    if isinstance(size, (tuple, list)):
+        nz, nx, ny = size
+        check(lib().vrt_output_create_regular(str(output_path).encode(), int(nλ), int(nz), int(nx), int(ny), int(maxiter), C.byref(h)))
+    else:
+        check(lib().vrt_output_create(str(output_path).encode(), int(nλ), int(size), int(maxiter), C.byref(h)))
+    return OutputFile(h, str(output_path))
+
+
+def write_to_file(what, out, *args):
+    """the write_to_file methods of src/io.jl:57-157 on an OutputFile: VoronoiSites / HydrogenicLine / (difference, iteration) /
+    (n, field) / a source-function or population array"""
+    if isinstance(what, VoronoiSites):
+        out.write("positions", what.positions)
+        for f in ("temperature", "electron_density", "hydrogen_populations", "velocity_z", "velocity_x", "velocity_y"):
+            out.write(f, getattr(what, f))
+        out.write("boundaries", np.array([what.z_min, what.z_max, what.x_min, what.x_max, what.y_min, what.y_max], dtype=np.float64))
+    elif isinstance(what, HydrogenicLine):
+        out.write("wavelength", what.λ)
+        out.write("line_center", np.array([what.λ0]))
+    elif isinstance(what, float) and args:
+        out.write_convergence(args[0], what)
+    elif isinstance(what, (int, np.integer)) and args:
+        out.write(args[0], np.array([what], dtype=np.int64))
+    else:
+        a = np.asarray(what)
+        out.write("populations" if a.shape[-1] == 3 and a.ndim in (2, 4) else "source_function", a)
+
+
 def nccl_unique_id():
     """128 bytes to be handed to every member of a process group (vrt_nccl_unique_id)"""
     raw = C.create_string_buffer(128)

@@ -27,6 +27,10 @@ __host__ __device__ __forceinline__ cplx c_div(cplx a, cplx b) {
     double den = b.re * b.re + b.im * b.im;
     return {(a.re * b.re + a.im * b.im) / den, (a.im * b.re - a.re * b.im) / den};
 }
+// Re(a / b): one division (the Voigt function only needs the real part of the Faddeeva function)
+__host__ __device__ __forceinline__ double c_div_re(cplx a, cplx b) {
+    return (a.re * b.re + a.im * b.im) / (b.re * b.re + b.im * b.im);
+}
 
 // Re w(v + i a), Humlíček (1982) w4 — what Transparency.jl's voigt_profile evaluates
 // (call sites: reference src/line.jl:133, src/rates.jl:408).
@@ -37,7 +41,7 @@ __device__ __forceinline__ double humlicek_re(double a, double v) {
         cplx zz = c_mul(z, z);
         cplx den = {zz.re - 0.5, zz.im};
         cplx num = {-INV_SQRT_PI * z.im, INV_SQRT_PI * z.re};
-        return c_div(num, den).re;
+        return c_div_re(num, den);
     } else if (s > 5.5) {
         cplx zz = c_mul(z, z);
         cplx t1 = {zz.re * INV_SQRT_PI - 1.4104739589, zz.im * INV_SQRT_PI};
@@ -45,7 +49,7 @@ __device__ __forceinline__ double humlicek_re(double a, double v) {
         cplx num = {-zt.im, zt.re};
         cplx zz3 = {zz.re - 3.0, zz.im};
         cplx den = c_add_r(0.75, c_mul(zz, zz3));
-        return c_div(num, den).re;
+        return c_div_re(num, den);
     } else {
         double x = v, y = a;
         cplx t = {y, -x};
@@ -59,7 +63,7 @@ __device__ __forceinline__ double humlicek_re(double a, double v) {
             den = c_add_r(39.27121, c_mul(t, den));
             den = c_add_r(38.82363, c_mul(t, den));
             den = c_add_r(16.4955, c_mul(t, den));
-            return c_div(num, den).re;
+            return c_div_re(num, den);
         } else {
             cplx u = c_mul(t, t);
             cplx num = c_rsub(1.320522, c_scale(0.56419, u));
@@ -76,8 +80,7 @@ __device__ __forceinline__ double humlicek_re(double a, double v) {
             den = c_rsub(9022.23, c_mul(u, den));
             den = c_rsub(24322.8, c_mul(u, den));
             den = c_rsub(32066.6, c_mul(u, den));
-            cplx q = c_div(num, den);
-            return exp(u.re) * cos(u.im) - q.re;
+            return exp(u.re) * cos(u.im) - c_div_re(num, den);
         }
     }
 }

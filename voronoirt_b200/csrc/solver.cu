@@ -129,6 +129,9 @@ struct OpacityDirs {
 // CELLS at the SAME wavelength: the Humlíček region (|v| + a) is then almost warp-uniform, whereas lanes over
 // wavelengths (core .. far wing) would serialise all four regions.  The tile is transposed through shared memory
 // so that the α rows go out as coalesced fp64 row writes.
+// Per evaluation the only division left is the one inside the Faddeeva approximation: the damping parameter a(cell, λ) does
+// not depend on the direction and is kept in a second shared tile for all directions of the batch; 1/ΔD and the factor
+// hc/(4πλ0)·(n1 B12 − n2 B21)/(√π ΔD) are formed once per cell.  (v = Δλ·(1/ΔD) instead of Δλ/ΔD moves v by at most one ulp.)
 constexpr int OP_TC = 32;
 constexpr int OP_THREADS = 256;
 __global__ void __launch_bounds__(OP_THREADS) k_opacity(int64_t n, int64_t lc, const double* __restrict__ lam /* chunk */, LineDev L,
@@ -136,28 +139,29 @@ __global__ void __launch_bounds__(OP_THREADS) k_opacity(int64_t n, int64_t lc, c
                                                         const double* __restrict__ dD, const double* __restrict__ vz,
                                                         const double* __restrict__ vx, const double* __restrict__ vy,
                                                         const double* __restrict__ pops, const double* __restrict__ alpha_cont) {
-    extern __shared__ double tile[];                 // [OP_TC][ldt]
+    extern __shared__ double tile[];                 // [OP_TC][ldt] α of one direction, then [OP_TC][ldt] damping a
     const int ldt = (int)lc | 1;                     // odd row stride: conflict-light transposed writes
+    double* atile = tile + OP_TC * ldt;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = OP_THREADS / 32;
     for (int64_t c0 = (int64_t)blockIdx.x * OP_TC; c0 < n; c0 += (int64_t)gridDim.x * OP_TC) {
         const int64_t c = c0 + lane;
         const bool ok = c < n;
         const int64_t cc = ok ? c : n - 1;
         const double dd = dD[cc], g = gamma[cc];
-        const double pop = pops[cc] * L.Bij - pops[n + cc] * L.Bji;
+        const double rdd = 1.0 / dd;
+        const double scale = L.c_line * (pops[cc] * L.Bij - pops[n + cc] * L.Bji) / (sqrt(PI) * (dd * 1e-9));
         const double ac = alpha_cont[cc];
         const double v0 = vz[cc], v1 = vx[cc], v2 = vy[cc];
         const int ncell = (int)min((int64_t)OP_TC, n - c0);
+        // each thread fills and later reads its own entries of atile (same cell, same wavelengths): no barrier needed
+        for (int l = warp; l < lc; l += nwarp) atile[lane * ldt + l] = damping_param(g, lam[l], dd);
         for (int d = 0; d < D.nd; d++) {
             // line_of_sight_velocity(sites, -k) (line.jl:198-208); explicitly rounded like the oracle
             const double vlos = __dadd_rn(__dadd_rn(__dmul_rn(v0, -D.k[d][0]), __dmul_rn(v1, -D.k[d][1])), __dmul_rn(v2, -D.k[d][2]));
             const double shift = __ddiv_rn(__dmul_rn(L.lambda0, vlos), C_0);
             for (int l = warp; l < lc; l += nwarp) {
-                const double lm = lam[l];
-                const double a = damping_param(g, lm, dd);
-                const double v = __ddiv_rn(__dadd_rn(__dadd_rn(lm, -L.lambda0), shift), dd);
-                const double prof = voigt_profile(a, v, dd * 1e-9);
-                tile[lane * ldt + l] = L.c_line * prof * pop + ac;
+                const double v = __dmul_rn(__dadd_rn(__dadd_rn(lam[l], -L.lambda0), shift), rdd);
+                tile[lane * ldt + l] = fma(humlicek_re(atile[lane * ldt + l], v), scale, ac);
             }
             __syncthreads();
             double* __restrict__ out = D.alpha[d] + c0 * lc;
@@ -615,6 +619,7 @@ static int plan_buffers(vrt_solver* s) {
         int64_t lc = 0;
         VRT_TRY(regular_plan_chunk(s->g, s->nlam, s->is_line ? 1.0 : 0.0, &lc));
         if (s->cfg.lam_chunk > 0) lc = std::min<int64_t>(lc, s->cfg.lam_chunk);
+        if (s->is_line) lc = std::min<int64_t>(lc, 384);   // two opacity tiles per CTA in shared memory
         const int64_t passes = (s->nlam + lc - 1) / lc;
         lc = (s->nlam + passes - 1) / passes;
         s->lc = lc;
@@ -648,8 +653,10 @@ static int plan_buffers(vrt_solver* s) {
         rows_max = std::max(rows_max, per_dir_rows(d));
     }
     int64_t lc = s->cfg.lam_chunk > 0 ? std::min<int64_t>(s->cfg.lam_chunk, s->nlam) : s->nlam;
+    // the opacity kernel keeps two OP_TC x lc tiles in shared memory (227 KB per CTA at most): wider chunks are split
+    if (s->is_line) lc = std::min<int64_t>(lc, 384);
     const char* envl = getenv("VRT_LAM_CHUNK");
-    if (envl && atoi(envl) > 0) lc = std::min<int64_t>(atoi(envl), s->nlam);
+    if (envl && atoi(envl) > 0) lc = std::min<int64_t>(atoi(envl), std::min<int64_t>(s->nlam, s->is_line ? 384 : s->nlam));
     int db = std::min(s->nd, MAX_DIRS);
     const char* env = getenv("VRT_MAX_DIRS");
     if (env && atoi(env) > 0) db = std::min(db, atoi(env));
@@ -772,7 +779,7 @@ static int mean_intensity_internal(vrt_solver* s, SweepStats* stats, double* t_o
                     for (int a = 0; a < 3; a++) od.k[0][a] = s->qk[d][a];
                     od.alpha[0] = s->alpha_p[0];
                     VRT_CUDA(cudaEventRecord(e0));
-                    const size_t shm = sizeof(double) * OP_TC * (size_t)((int)lc | 1);
+                    const size_t shm = 2 * sizeof(double) * OP_TC * (size_t)((int)lc | 1);
                     const int grid = (int)std::min<int64_t>((n + OP_TC - 1) / OP_TC, 148 * 16);
                     if (shm > 48 * 1024) VRT_CUDA(cudaFuncSetAttribute(k_opacity, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
                     k_opacity<<<grid, OP_THREADS, shm>>>(n, lc, s->lam_dev.p + s->l_begin + l0, s->ld, od, s->gamma.p, s->dD.p, s->vz.p,
@@ -843,7 +850,7 @@ static int mean_intensity_internal(vrt_solver* s, SweepStats* stats, double* t_o
                 op_ev.emplace_back(o0, o1);
                 VRT_CUDA(cudaEventRecord(o0));
                 {
-                    const size_t shm = sizeof(double) * OP_TC * (size_t)((int)lc | 1);
+                    const size_t shm = 2 * sizeof(double) * OP_TC * (size_t)((int)lc | 1);
                     const int grid = (int)std::min<int64_t>((n + OP_TC - 1) / OP_TC, 148 * 16);
                     if (shm > 48 * 1024) VRT_CUDA(cudaFuncSetAttribute(k_opacity, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
                     k_opacity<<<grid, OP_THREADS, shm>>>(n, lc, s->lam_dev.p + s->l_begin + l0, s->ld, od, s->gamma.p, s->dD.p, s->vz.p,
@@ -1389,6 +1396,58 @@ int vrt_get_state(vrt_solver* s, double* S, double* J, double* populations) {
         if (o != populations) VRT_TRY(copy_out(populations, o, sizeof(double) * 3 * n));
     }
     VRT_CUDA(cudaDeviceSynchronize());
+    return VRT_OK;
+}
+
+// dst[i][l] = src[rank_of[i]][l]: rows of `cnt` consecutive sites in host site order out of the internal order
+__global__ void k_gather_sites(const double* __restrict__ src, double* __restrict__ dst, const int32_t* __restrict__ rank_of,
+                               int64_t cnt, int64_t nlam) {
+    const int64_t total = cnt * nlam;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / nlam, l = i - r * nlam;
+        dst[i] = src[(int64_t)rank_of[r] * nlam + l];
+    }
+}
+
+// write_to_file(S_λ, output_path) and write_to_file(populations, output_path) (io.jl:57-83): what Λ_voronoi does after every
+// iteration (lambda_iteration.jl:280-281), straight from the device state: site-ordered row blocks are gathered on the
+// device, copied into a pinned staging buffer and written at their place in the datasets.  Needs every wavelength on this
+// process (no wavelength shard).
+int vrt_output_write_state(vrt_outfile* f, vrt_solver* s) {
+    if (!f || !s) return VRT_E_INVALID;
+    VRT_TRY(ensure_state(s));
+    int64_t fn = 0, fl = 0;
+    VRT_TRY(outfile_shape(f, &fn, &fl));
+    const int64_t n = s->n;
+    if (fn != n || fl != s->nlam || s->nlam != s->nlam_total) {
+        set_error("vrt_output_write_state: the file was created for %lld sites x %lld wavelengths, the solver holds %lld x %lld", (long long)fn,
+                  (long long)fl, (long long)n, (long long)s->nlam);
+        return VRT_E_INVALID;
+    }
+    const int64_t rows = std::max<int64_t>(1, std::min<int64_t>(n, ((int64_t)64 << 20) / (8 * s->nlam)));
+    DevBuf<double> dev;
+    VRT_TRY(dev.alloc((size_t)rows * s->nlam));
+    double* pin[2] = {nullptr, nullptr};
+    struct Pins { double** p; ~Pins() { for (int i = 0; i < 2; i++) if (p[i]) cudaFreeHost(p[i]); } } pins{pin};
+    for (int i = 0; i < 2; i++) VRT_CUDA(cudaMallocHost((void**)&pin[i], sizeof(double) * (size_t)rows * s->nlam));
+    int b = 0;
+    for (int64_t i0 = 0; i0 < n; i0 += rows, b ^= 1) {
+        const int64_t cnt = std::min(rows, n - i0);
+        k_gather_sites<<<nblocks(cnt * s->nlam, 256), 256>>>(s->S.p, dev.p, s->g->rank_of.p + i0, cnt, s->nlam);
+        VRT_CUDA(cudaGetLastError());
+        VRT_CUDA(cudaMemcpy(pin[b], dev.p, sizeof(double) * (size_t)cnt * s->nlam, cudaMemcpyDeviceToHost));
+        VRT_TRY(outfile_write_at(f, "source_function", (uint64_t)i0 * s->nlam * 8, pin[b], sizeof(double) * (size_t)cnt * s->nlam));
+    }
+    if (s->is_line) {
+        // populations (n_sites, 3) column-major: three site-ordered columns
+        std::vector<double> host((size_t)3 * n);
+        DevBuf<double> tmp;
+        VRT_TRY(tmp.alloc((size_t)3 * n));
+        k_scatter_cols<<<nblocks(n, 256), 256>>>(s->pops.p, tmp.p, s->g->site_of.p, n, 3);
+        VRT_CUDA(cudaGetLastError());
+        VRT_CUDA(cudaMemcpy(host.data(), tmp.p, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost));
+        VRT_TRY(outfile_write_at(f, "populations", 0, host.data(), sizeof(double) * 3 * n));
+    }
     return VRT_OK;
 }
 

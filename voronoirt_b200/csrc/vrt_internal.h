@@ -210,6 +210,10 @@ void comm_free(void* comm);
 cudaStream_t comm_stream(void* comm);
 int comm_op(void* comm, double* buf, int64_t count, int op, cudaStream_t st);
 
+// outfile.cu
+int outfile_write_at(vrt_outfile* f, const char* name, uint64_t offset, const void* host, size_t nbytes);
+int outfile_shape(const vrt_outfile* f, int64_t* n_sites, int64_t* nlam);
+
 // misc kernels (physics.cu)
 int permute_rows(const double* src, double* dst, const int32_t* map, int64_t n, int64_t nlam, int gather, cudaStream_t st);
 extern thread_local SweepStats g_last_stats;
