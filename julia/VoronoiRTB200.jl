@@ -249,6 +249,61 @@ function nearest_site(positions::Matrix{Float64}, bounds::Vector{Float64}, point
     return idx, dist
 end
 
+# ---------------------------------------------------------------- multi-GPU: collectives inside the library
+# One Julia process per GPU (e.g. under MPI.jl or Distributed).  The host only ferries the 128-byte unique id: rank 0 of a group
+# calls nccl_unique_id(), broadcasts the bytes with whatever it has (MPI.Bcast!, a socket, a file) and every member calls
+# comm_init! on its solver; libvrt.so then runs ncclCommInitRank and all collectives of the Λ-iteration itself.
+function nccl_unique_id()
+    id = Vector{UInt8}(undef, 128)
+    check(ccall((:vrt_nccl_unique_id, libvrt), Cint, (Ptr{UInt8},), id))
+    return id
+end
+function comm_init!(solver::Ptr{Cvoid}; dir_id=nothing, dir_rank=0, dir_size=1, lam_id=nothing, lam_rank=0, lam_size=1)
+    check(ccall((:vrt_solver_comm_init, libvrt), Cint, (Ptr{Cvoid}, Ptr{UInt8}, Int32, Int32, Ptr{UInt8}, Int32, Int32), solver,
+                dir_id === nothing ? C_NULL : pointer(dir_id), dir_rank, dir_size, lam_id === nothing ? C_NULL : pointer(lam_id), lam_rank, lam_size))
+end
+# this process's cells [first, last) in internal order (internal cell c is site perm_up[c+1]) and its slice of the state
+function cell_slice(solver::Ptr{Cvoid})
+    a = Ref{Int64}(0); b = Ref{Int64}(0)
+    check(ccall((:vrt_solver_cell_slice, libvrt), Cint, (Ptr{Cvoid}, Ref{Int64}, Ref{Int64}), solver, a, b))
+    return a[], b[]
+end
+function get_state_slice!(solver::Ptr{Cvoid}, S::Matrix{Float64}, J::Matrix{Float64}, populations::Matrix{Float64})
+    check(ccall((:vrt_get_state_slice, libvrt), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}), solver, S, J, populations))
+end
+function set_state_slice!(solver::Ptr{Cvoid}, S::Matrix{Float64}, populations::Matrix{Float64})
+    check(ccall((:vrt_set_state_slice, libvrt), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), solver, S, populations))
+end
+function state_checksum(solver::Ptr{Cvoid})
+    out = zeros(Float64, 4)
+    check(ccall((:vrt_state_checksum, libvrt), Cint, (Ptr{Cvoid}, Ptr{Float64}), solver, out))
+    return out
+end
+
+# ---------------------------------------------------------------- output file (src/io.jl:57-225) without HDF5.jl
+# create_output_file(output_path, nλ, n_sites, maxiter) -> handle; the write_to_file methods become write_dataset! calls and
+# the per-iteration writes of S and the populations (src/lambda_iteration.jl:280-281) one write_state! from the device.
+function create_output_file(output_path::String, nλ::Int, n_sites::Int, maxiter::Int)
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:vrt_output_create, libvrt), Cint, (Cstring, Int64, Int64, Int64, Ref{Ptr{Cvoid}}), output_path, nλ, n_sites, maxiter, h))
+    return h[]
+end
+function create_output_file(output_path::String, nλ::Int, atmosphere_size::Tuple, maxiter::Int)
+    nz, nx, ny = atmosphere_size
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:vrt_output_create_regular, libvrt), Cint, (Cstring, Int64, Int64, Int64, Int64, Int64, Ref{Ptr{Cvoid}}),
+                output_path, nλ, nz, nx, ny, maxiter, h))
+    return h[]
+end
+write_dataset!(out::Ptr{Cvoid}, name::String, a::Array{Float64}) =
+    check(ccall((:vrt_output_write, libvrt), Cint, (Ptr{Cvoid}, Cstring, Ptr{Cvoid}, Int64), out, name, a, sizeof(a)))
+write_dataset!(out::Ptr{Cvoid}, name::String, a::Array{Int64}) =
+    check(ccall((:vrt_output_write, libvrt), Cint, (Ptr{Cvoid}, Cstring, Ptr{Cvoid}, Int64), out, name, a, sizeof(a)))
+write_convergence!(out::Ptr{Cvoid}, iteration::Int, difference::Float64) =
+    check(ccall((:vrt_output_write_convergence, libvrt), Cint, (Ptr{Cvoid}, Int64, Float64), out, iteration, difference))
+write_state!(out::Ptr{Cvoid}, solver::Ptr{Cvoid}) = check(ccall((:vrt_output_write_state, libvrt), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), out, solver))
+close_output(out::Ptr{Cvoid}) = check(ccall((:vrt_output_close, libvrt), Cint, (Ptr{Cvoid},), out))
+
 function readdlm_quadrature(fname)
     rows = [parse.(Float64, split(l)) for l in eachline(fname) if !isempty(strip(l))]
     return permutedims(hcat(rows...))

@@ -495,7 +495,12 @@ __global__ void __launch_bounds__(32 * (TMA_NP + TMA_NC), 3) k_sweep_tma(const S
                     np = 0;
                 }
                 for (;;) {
-                    mbar_wait(full + stage, par);
+                    // experiment 8: plain timed polling instead of try_wait (whose SYNCS wake-up fires on every mbarrier
+                    // event of the CTA: ~100 wake-ups per visit in the ncu source view)
+                    if (P.experiment == 8) {
+                        while (!mbar_test(full + stage, par)) __nanosleep(256);
+                    } else
+                        mbar_wait(full + stage, par);
                     if (reinterpret_cast<volatile StageHdr*>(hdr)[stage].seq == it) break;
                     __nanosleep(64);
                 }
