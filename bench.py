@@ -378,12 +378,30 @@ def main():
     sites = V.VoronoiSites(*cell, atm["temperature"], atm["electron_density"], atm["hydrogen_density"], atm["velocity_z"],
                            atm["velocity_x"], atm["velocity_y"], b["z_min"], b["z_max"], b["x_min"], b["x_max"], b["y_min"], b["y_max"], n)
     ndirs = int(np.sum(th != 90))
-    mine = assign_directions(sites, w, th, ph, D, di)
-    my_quad = (w[mine], th[mine], ph[mine]) if D > 1 else P["qpath"]
-    dlo, dhi = 0, len(mine)
-    solver = V.Solver(sites, my_quad, line=line, α_cont=α_cont, ελ=ελ, C_rates=Cr, LTE_pops=lte,
-                      lam_range=(lo, hi) if G > 1 else None, dir_range=(dlo, dhi) if D > 1 else None,
-                      cell_shard=(di, D) if D > 1 and not os.environ.get("VRT_NO_CELL_SHARD") else None)
+    def make_solver(mine):
+        my_quad = (w[mine], th[mine], ph[mine]) if D > 1 else P["qpath"]
+        return V.Solver(sites, my_quad, line=line, α_cont=α_cont, ελ=ελ, C_rates=Cr, LTE_pops=lte,
+                        lam_range=(lo, hi) if G > 1 else None, dir_range=(0, len(mine)) if D > 1 else None,
+                        cell_shard=(di, D) if D > 1 and not os.environ.get("VRT_NO_CELL_SHARD") else None)
+    mine = round_robin(int(nq), D, di)
+    solver = make_solver(mine)
+    balance = None
+    if D > 1 and not os.environ.get("VRT_ROUND_ROBIN"):
+        # balance the direction shards by the measured work of each direction (visits of its sweep program): every rank
+        # reports the directions it built, the table is all-gathered, and the shards are re-dealt longest-first
+        cost = torch.zeros(int(nq), dtype=torch.float64, device="cuda")
+        cost[torch.as_tensor(mine, device="cuda")] = torch.as_tensor(solver.direction_visits(), device="cuda")
+        dist.all_reduce(cost, op=dist.ReduceOp.MAX)
+        costs = cost.cpu().numpy()
+        shards, load = lpt_assign(list(costs), D)
+        rr_load = [float(costs[round_robin(int(nq), D, r)].sum()) for r in range(D)]
+        balance = {"how": "longest processing time first on the visits of each direction's sweep program",
+                   "max_over_mean_load": max(load) / (sum(load) / D), "round_robin_max_over_mean_load": max(rr_load) / (sum(rr_load) / D)}
+        if not np.array_equal(shards[di], mine):
+            solver.close()
+            _lib.check(_lib.lib().vrt_grid_release_schedules(sites._grid.h))
+            mine = shards[di]
+            solver = make_solver(mine)
     coll = {"ms": 0.0, "bytes": 0}
     comm_how = None
     if world > 1:
@@ -538,7 +556,7 @@ def main():
                "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "strong",
                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                "config": {"workload": workload_name(args.workload, P, nlam), "sites": n, "quadrature": P["qname"], "n_dirs": ndirs, "n_lambda": nlam,
-                          "parallelism": f"{D} direction shards x {G} wavelength shards; {comm_how}" if world > 1 else "single GPU", "l2_policy": "inputs larger than L2 "
+                          "parallelism": f"{D} direction shards x {G} wavelength shards; {comm_how}" if world > 1 else "single GPU", "direction_balance": balance, "l2_policy": "inputs larger than L2 "
                           f"(S+J+I+alpha = {8 * n * nlam * (2 + 2 * ndirs) / 1e9:.1f} GB)", "n_sweeps": 3, "p": 7.0,
                           "visit_order": os.environ.get("VRT_BLOCKS", "default") + "/" + os.environ.get("VRT_SLAB", "default")},
                "s_per_lambda_iteration": ms_max / K / 1e3, "roofline": roofline, "cpu_baseline": cpu, "parity": parity, "checksum": checksum,
@@ -553,13 +571,21 @@ def main():
     return 0
 
 
-def assign_directions(sites, w, th, ph, D, di):
-    """directions of rank di of D direction shards.  Round-robin deal (rank di takes di, di+D, ...): neighbouring lines of the
-    quadrature files are up/down pairs of similar inclination, so every rank gets a similar mix of steep and grazing rays."""
-    nq = len(w)
-    if D <= 1:
-        return np.arange(nq)
-    return np.arange(di, nq, D)
+def lpt_assign(costs, D):
+    """longest processing time first: directions in descending cost to the least loaded of D shards -> list of index arrays"""
+    order = sorted(range(len(costs)), key=lambda i: (-costs[i], i))
+    load = [0.0] * D
+    out = [[] for _ in range(D)]
+    for i in order:
+        r = min(range(D), key=lambda j: (load[j], j))
+        out[r].append(i)
+        load[r] += costs[i]
+    return [np.array(sorted(v), dtype=np.int64) for v in out], load
+
+
+def round_robin(nq, D, di):
+    """rank di takes di, di+D, ...: neighbouring lines of the quadrature files are up/down pairs of similar inclination"""
+    return np.arange(di, nq, D) if D > 1 else np.arange(nq)
 
 
 def attach_collectives(solver, dist, torch, local_rank, rank, world, D, G, di, gi, coll):
@@ -936,11 +962,12 @@ def regular_problem(nz, nx, ny, nbb, nbf):
 
 
 def main_regular(args, W, K):
-    """BASELINE configs[3]: NLTE line Λ-iteration on the regular grid (Λ_regular, lambda_iteration.jl:116-205), one GPU."""
+    """BASELINE configs[3]: NLTE line Λ-iteration on the regular grid (Λ_regular, lambda_iteration.jl:116-205).  N > 1: the
+    directions of the quadrature are sharded over the ranks (contiguous ranges), J is all-reduced inside the library."""
     rank = int(os.environ.get("RANK", "0"))
-    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
-        if rank == 0:
-            print(json.dumps({"workload": args.workload, "unavailable": "the regular-grid path is single-GPU this round (replicas only)"}))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference" and rank != 0:
         return 0
     base, kx, ky, qname, nbb, nbf = WORKLOADS[args.workload]
     shape = tuple(int(v) for v in os.environ.get("VRT_REG_SHAPE", "400,258,258").split(","))
@@ -992,7 +1019,13 @@ def main_regular(args, W, K):
     import torch
     import voronoirt_b200 as V
     from voronoirt_b200 import _lib
-    torch.cuda.set_device(0)
+    torch.cuda.set_device(local_rank)
+    _lib.check(_lib.lib().vrt_set_device(local_rank))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("NCCL_DEBUG", "WARN")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     t_setup = time.time()
     Q = regular_problem(*shape, nbb, nbf)
     line, n, f = Q["line"], Q["n"], Q["fields"]
@@ -1000,21 +1033,52 @@ def main_regular(args, W, K):
     atm = V.Atmosphere(Q["z"], Q["x"], Q["y"], f["temperature"], f["electron_density"], f["hydrogen_density"], f["velocity_z"],
                        f["velocity_x"], f["velocity_y"])
     lam_chunk = int(os.environ.get("VRT_REG_BENCH_CHUNK", "0"))   # 0: as many wavelengths per pass as the free HBM allows
-    solver = V.Solver(atm, qpath, line=line, α_cont=Q["α_cont"], ελ=Q["ελ"], C_rates=Q["C"], LTE_pops=Q["lte"], lam_chunk=lam_chunk)
-    log(f"setup {time.time() - t_setup:.1f}s: regular grid {shape} = {n} cells, dirs={ndirs} nlam={nlam}")
+    D = min(world, int(nq))
+    dlo, dhi = shard_range(int(nq), D, rank % D)
+    solver = V.Solver(atm, qpath, line=line, α_cont=Q["α_cont"], ελ=Q["ελ"], C_rates=Q["C"], LTE_pops=Q["lte"], lam_chunk=lam_chunk,
+                      dir_range=(dlo, dhi) if world > 1 else None)
+    comm_how = None
+    if world > 1:
+        comm_how = attach_collectives(solver, dist, torch, local_rank, rank, world, D, 1, rank % D, 0, {"ms": 0.0, "bytes": 0})
+    log(f"setup {time.time() - t_setup:.1f}s: regular grid {shape} = {n} cells, dirs={ndirs} nlam={nlam}, rank 0 directions [{dlo},{dhi})")
+
+    def sync():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
     solver.iterate(-1.0, W)
-    torch.cuda.synchronize()
-    sampler = ClockSampler(0)
+    sync()
+    sampler = ClockSampler(local_rank)
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     res = solver.iterate(-1.0, K)
     e1.record()
-    torch.cuda.synchronize()
+    sync()
     clocks = sampler.stop()
-    ms = e0.elapsed_time(e1)
+    tt = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    ms = float(tt[0])
     stats = _lib.last_stats()
     hist = res["history"]
+    checksum = solver.checksum()
+    if rank != 0 or world > 1:
+        # N > 1: device-resident line only (the end-to-end and CPU legs are reported at N = 1)
+        if rank == 0:
+            interior = float(shape[0] - 1) * (shape[1] - 2) * (shape[2] - 2)
+            updates = interior * ndirs * nlam
+            print(json.dumps({"metric": metric, "value": updates / (ms / K / 1e3), "unit": "updates/s", "n_gpus": world, "steps": K, "warmup": W,
+                              "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                              "config": {"workload": f"{args.workload}: NLTE line Lambda-iteration on the regular grid {shape}, {qname}, {nlam} wavelengths",
+                                         "parallelism": f"{D} direction shards; {comm_how}"},
+                              "checksum": checksum, "gpu_launches": int(max(stats["kernels"], 1)), "clocks": clocks, "e2e": None, "cpu_baseline": None,
+                              "roofline": None}))
+        solver.close()
+        if dist is not None:
+            dist.destroy_process_group()
+        return 0
     interior = float(shape[0] - 1) * (shape[1] - 2) * (shape[2] - 2)
     updates = interior * ndirs * nlam
     value = updates / (ms / K / 1e3)

@@ -266,8 +266,9 @@ int vrt_regular_lambda_iterate(int64_t nz, int64_t nx, int64_t ny, const double*
  * vrt_calculate_R (rates.jl:96-143), vrt_lambda_iterate (Λ_regular, lambda_iteration.jl:116-205 with criterion :299-323),
  * vrt_get_state / vrt_set_state — with every per-site array being the flattened (nz, nx, ny) array, S and J
  * nlam x nz x nx x ny, populations nz x nx x ny x 3.  The formal solutions run through the plane walk of
- * vrt_regular_formal_solve.  Layer / stencil / schedule queries and direction or cell shards return VRT_E_STATE /
- * VRT_E_INVALID on such a handle.  Destroy with vrt_grid_destroy. */
+ * vrt_regular_formal_solve.  Layer / stencil / schedule queries and cell shards return VRT_E_STATE /
+ * VRT_E_INVALID on such a handle; direction and wavelength shards work as on a Voronoi grid (J is all-reduced over the
+ * direction group).  Destroy with vrt_grid_destroy. */
 int vrt_regular_grid_create(int64_t nz, int64_t nx, int64_t ny, const double* z, const double* x, const double* y, vrt_grid** out);
 
 /* the regular-grid entries keep their device workspace (3-6 internal copies of one wavelength chunk) between calls;
@@ -301,6 +302,11 @@ int vrt_nccl_version(int32_t* version);
 int vrt_nccl_unique_id(char id[128]);
 int vrt_solver_comm_init(vrt_solver* s, const char* dir_id, int32_t dir_rank, int32_t dir_size,
                          const char* lam_id, int32_t lam_rank, int32_t lam_size);
+
+/* Work of each direction this solver holds, as the number of (cell, sweep) visits of its sweep program, in the order of the
+ * solver's quadrature table without the θ = 90 rows.  visits may be NULL to query n_dirs.  A host that shards the directions
+ * over processes balances them with it (longest processing time first) instead of dealing them round-robin. */
+int vrt_solver_direction_visits(const vrt_solver* s, int64_t* n_dirs, double* visits, int64_t capacity);
 
 /* (Re)upload one per-site input of the line solver.  In the reference these are plain function arguments
  * (α_cont of J_λ_voronoi, LTE_pops of calculate_R, C of get_revised_populations), so a drop-in caller may

@@ -25,10 +25,11 @@ def run(args, env=None):
 @pytest.mark.parametrize("args,env", [
     (["--impl", "reference", "--workload", "small", "--steps", "1", "--warmup", "0"], None),
     (["--impl", "reference", "--workload", "regular_400", "--steps", "1", "--warmup", "0"], {"VRT_REG_SHAPE": "20,14,14"}),
+    (["--impl", "reference", "--workload", "searchlight", "--steps", "1", "--warmup", "0"], None),
 ])
 def test_reference_arm_prints_one_contract_line(args, env):
-    staged = os.path.exists(os.path.join(ROOT, "oracle", "_ref", "output_sites")) or os.path.exists("/root/reference/rt_preprocessing/output_sites")
-    if args[3] == "small" and not staged:
+    staged = os.path.exists(os.path.join(ROOT, "baseline", "_ref", "output_sites")) or os.path.exists("/root/reference/rt_preprocessing/output_sites")
+    if args[3] in ("small", "searchlight") and not staged:
         pytest.skip("voro++ driver not staged")
     d = run(args, env)
     assert KEYS <= set(d) and d["impl"] == "reference"
@@ -36,3 +37,5 @@ def test_reference_arm_prints_one_contract_line(args, env):
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"]
+    if args[3] != "regular_400":
+        assert d["libvrt_mapped"] is False               # the CPU arm never loads the product library

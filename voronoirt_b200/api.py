@@ -581,6 +581,14 @@ class Solver:
         """in-library NCCL collectives (include/vrt.h vrt_solver_comm_init); ids are the 128 bytes of nccl_unique_id()"""
         check(lib().vrt_solver_comm_init(self.h, dir_id, int(dir_rank), int(dir_size), lam_id, int(lam_rank), int(lam_size)))
 
+    def direction_visits(self):
+        """(cell, sweep) visits of each direction this solver holds (θ = 90 rows left out): the cost used to balance direction shards"""
+        nd = C.c_int64()
+        check(lib().vrt_solver_direction_visits(self.h, C.byref(nd), None, 0))
+        out = (C.c_double * max(nd.value, 1))()
+        check(lib().vrt_solver_direction_visits(self.h, C.byref(nd), out, nd.value))
+        return np.array(out[:nd.value])
+
     def cell_slice(self):
         """[first, last) of the cells this process owns, in internal order (site perm_up[c])"""
         a, b = C.c_int64(), C.c_int64()

@@ -592,8 +592,8 @@ static int solver_common_init(vrt_solver* s, vrt_grid* g, const vrt_quadrature* 
     s->nd = (int)s->qk.size();
     s->n1_up = g->off_up[1] - 1;
     s->n1_dn = g->off_down[1] - 1;
-    if (g->regular && (s->cell_R > 1 || s->dir_sharded)) {
-        set_error("solver: direction / cell shards are not implemented on the regular grid");
+    if (g->regular && s->cell_R > 1) {
+        set_error("solver: cell shards are not implemented on the regular grid (direction and wavelength shards are)");
         return VRT_E_INVALID;
     }
     VRT_TRY(s->diff_bits.alloc(1));
@@ -809,6 +809,8 @@ static int mean_intensity_internal(vrt_solver* s, SweepStats* stats, double* t_o
         }
         if (s->nd == 0) VRT_CUDA(cudaMemset(s->J.p, 0, sizeof(double) * (size_t)n * s->nlam));
         VRT_CUDA(cudaDeviceSynchronize());
+        // direction shards (J_λ_regular's loop over the quadrature, lambda_iteration.jl:23-55, split over processes): J = Σ shards
+        if (s->dir_sharded && s->has_exchange()) VRT_TRY(exchange(s, s->J.p, n * s->nlam, 2));
         if (t_opacity_ms) *t_opacity_ms = opacity_ms;
         if (t_sweep_ms) *t_sweep_ms = stats->sweep_ms;
         return VRT_OK;
@@ -1506,6 +1508,21 @@ int vrt_solver_comm_init(vrt_solver* s, const char* dir_id, int32_t dir_rank, in
         s->comm = nullptr;
     }
     return comm_create(dir_id, dir_rank, dir_size, lam_id, lam_rank, lam_size, &s->comm);
+}
+
+// cost of each direction this solver holds (in the order of its quadrature table, θ = 90 rows left out): the number of
+// (cell, sweep) visits of its sweep program.  Hosts use it to balance direction shards (longest processing time first).
+int vrt_solver_direction_visits(const vrt_solver* s, int64_t* n_dirs, double* visits, int64_t capacity) {
+    if (!s || !n_dirs) return VRT_E_INVALID;
+    *n_dirs = s->nd;
+    if (visits) {
+        if (capacity < s->nd) {
+            set_error("vrt_solver_direction_visits: capacity %lld < %d directions", (long long)capacity, s->nd);
+            return VRT_E_INVALID;
+        }
+        for (int d = 0; d < s->nd; d++) visits[d] = s->sch[d] ? (double)s->sch[d]->n_visits : (double)s->n;
+    }
+    return VRT_OK;
 }
 
 int vrt_solver_cell_slice(const vrt_solver* s, int64_t* first, int64_t* last) {
