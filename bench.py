@@ -1137,8 +1137,9 @@ def workload_name(key, P, nlam):
     kx, ky = P["tiles"]
     tile = f" (voro++ tessellation of {P['base']} sites tiled {kx}x{ky} periodically)" if kx * ky > 1 else ""
     if P.get("native"):
-        tile = " (sampled directly, tessellated on the GPU by vrt_voronoi_neighbours)"
-    return f"{key}: NLTE line Lambda-iteration, {P['n']} Voronoi sites{tile}, {P['qname']}, {nlam} wavelengths, synthetic Bifrost-shaped atmosphere"
+        tile = " (sampled from the atmosphere cube and tessellated on the GPU: vrt_rejection_sampling, vrt_voronoi_neighbours, vrt_trilinear)"
+    nsites = WORKLOADS[key][0] * kx * ky
+    return f"{key}: NLTE line Lambda-iteration, {nsites} Voronoi sites{tile}, {P['qname']}, {nlam} wavelengths, synthetic Bifrost-shaped atmosphere"
 
 
 def _abi_null_cb():

@@ -160,7 +160,9 @@ def test_two_rank_direction_shards_match_single_gpu(mode):
     for r in (r0, r1):                                   # both ranks hold the full, identical state
         assert rel(r["S"], S1) < 1e-12 and rel(r["J"], J1) < 1e-12
         assert np.all(np.abs(r["pops"] - p1) <= 1e-9 * np.abs(p1) + 1e-13 * sites.hydrogen_populations[:, None])
-        assert np.allclose(r["diffs"], [h["diff"] for h in rres["history"]], rtol=1e-9)
+        # two iterations, the cell-sliced checkpoint round trip, one more iteration: the criterion of a fresh
+        # vrt_lambda_iterate call starts from S_old = 0 (lambda_iteration.jl:241), so its first value is 1
+        assert np.allclose(r["diffs"][:2], [h["diff"] for h in rres["history"]][:2], rtol=1e-9) and r["diffs"][2] == 1.0
         assert abs(r["checksum"]["sum_S"] / chk1["sum_S"] - 1) < 1e-12 and abs(r["checksum"]["sum_populations"] / chk1["sum_populations"] - 1) < 1e-12
     assert np.array_equal(r0["S"], r1["S"])
     # the cell slices tile the cells and are rows of S in internal (perm_up) order
