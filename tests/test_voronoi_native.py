@@ -227,3 +227,37 @@ def test_gpu_nearly_empty_periodic_boxes():
     for pos, gold in tiny_cases():
         nbr = V.voronoi_neighbours(pos, 0.0, 1.0, 0.0, 1.0, 0.0, 1.0)
         assert same_sets(np.asarray(nbr), gold), pos.shape
+
+
+def _lattice(m):
+    ax = (np.arange(m) + 0.5) / m
+    Z, X, Y = np.meshgrid(ax, ax, ax, indexing="ij")
+    pos = np.asfortranarray(np.stack([Z.ravel(), X.ravel(), Y.ravel()]))
+    idx = np.arange(m ** 3).reshape(m, m, m)                       # site id - 1 of lattice point (iz, ix, iy)
+    want = []
+    for iz in range(m):
+        for ix in range(m):
+            for iy in range(m):
+                row = [idx[iz, (ix + 1) % m, iy] + 1, idx[iz, (ix - 1) % m, iy] + 1, idx[iz, ix, (iy + 1) % m] + 1, idx[iz, ix, (iy - 1) % m] + 1]
+                row.append(idx[iz - 1, ix, iy] + 1 if iz > 0 else -5)
+                row.append(idx[iz + 1, ix, iy] + 1 if iz < m - 1 else -6)
+                want.append(sorted(row))
+    return pos, want
+
+
+def test_cubic_lattice_has_six_faces_per_cell(harness):
+    """exactly degenerate input: the bisectors towards edge and corner neighbours only touch the cell; those zero-area faces
+    are dropped, as voro++ drops them (6 faces per cell: periodic in x and y, walls in z)"""
+    pos, want = _lattice(6)
+    nbr, st, bad = run_harness(harness, pos, np.array([0.0, 1.0, 0.0, 1.0, 0.0, 1.0]))
+    assert bad == 0 and np.all(nbr[:, 0] == 6)
+    assert [sorted(nbr[i, 1:7].tolist()) for i in range(nbr.shape[0])] == want
+
+
+@pytest.mark.gpu
+def test_gpu_cubic_lattice_has_six_faces_per_cell():
+    import voronoirt_b200 as V
+    pos, want = _lattice(8)
+    nbr = np.asarray(V.voronoi_neighbours(pos, 0.0, 1.0, 0.0, 1.0, 0.0, 1.0))
+    assert np.all(nbr[:, 0] == 6)
+    assert [sorted(nbr[i, 1:7].tolist()) for i in range(nbr.shape[0])] == want

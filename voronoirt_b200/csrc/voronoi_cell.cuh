@@ -174,12 +174,32 @@ struct ConvexCell {
         return true;
     }
 
-    // planes that still own a vertex = faces of the cell; ids written in plane order; returns the count
+    // planes that still own a vertex = faces of the cell; ids written in plane order; returns the count.
+    // A face whose vertices are (nearly) collinear has no area: it is the trace of a bisector that only touches an edge
+    // or a corner of the cell (lattice-aligned sites) and is dropped, like voro++ drops it.
     VC_HD int faces(int64_t* out, int cap) const {
         int n = 0;
+        const double eps2 = 1e-24 * r2max;   // (1e-12 of the cell radius)^2
         for (int p = 0; p < np; p++) {
             bool used = false;
-            for (int t = 0; t < nt && !used; t++) used = t0[t] == p || t1[t] == p || t2[t] == p;
+            double ax = 0, ay = 0, az = 0, bx = 0, by = 0, bz = 0, far2 = 0;
+            int first = -1;
+            for (int t = 0; t < nt; t++) {
+                if (!(t0[t] == p || t1[t] == p || t2[t] == p)) continue;
+                if (first < 0) { first = t; ax = vx[t]; ay = vy[t]; az = vz[t]; continue; }
+                const double ex = vx[t] - ax, ey = vy[t] - ay, ez = vz[t] - az;
+                const double d2 = ex * ex + ey * ey + ez * ez;
+                if (d2 > far2) { far2 = d2; bx = ex; by = ey; bz = ez; }
+            }
+            if (first >= 0 && far2 > eps2) {
+                // height of the remaining vertices over the line a -> a + b
+                for (int t = 0; t < nt && !used; t++) {
+                    if (!(t0[t] == p || t1[t] == p || t2[t] == p)) continue;
+                    const double ex = vx[t] - ax, ey = vy[t] - ay, ez = vz[t] - az;
+                    const double cx = ey * bz - ez * by, cy = ez * bx - ex * bz, cz = ex * by - ey * bx;
+                    used = (cx * cx + cy * cy + cz * cz) > eps2 * far2;   // |e x b|^2 = h^2 |b|^2
+                }
+            }
             if (used) {
                 if (n < cap) out[n] = pid[p];
                 n++;
