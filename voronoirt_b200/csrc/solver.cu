@@ -502,6 +502,8 @@ struct vrt_solver {
     void* allreduce_user = nullptr;
     void* comm = nullptr;                   // in-library NCCL communicators (comm.cu), preferred over the host hook
     cudaEvent_t comm_ev[2] = {nullptr, nullptr};
+    cudaEvent_t gather_ev = nullptr;        // a deferred all-gather of S is running on the collectives' stream until this event
+    bool gather_pending = false;
     bool has_exchange() const { return comm != nullptr || allreduce != nullptr; }
     // CUDA events are created once and reused (no create/destroy per iteration, nothing to leak on an early return)
     std::vector<cudaEvent_t> ev_pool;
@@ -520,6 +522,7 @@ struct vrt_solver {
         for (auto e : ev_pool) cudaEventDestroy(e);
         for (auto e : comm_ev)
             if (e) cudaEventDestroy(e);
+        if (gather_ev) cudaEventDestroy(gather_ev);
         if (comm) vrt::comm_free(comm);
     }
 };
@@ -736,6 +739,30 @@ static int exchange(vrt_solver* s, double* buf, int64_t count, int op) {
     return VRT_OK;
 }
 
+// The all-gather of S at the end of an iteration is not needed until the next sweep: with in-library collectives it is only
+// enqueued on the collectives' stream, and whoever reads S beyond the own cell slice calls wait_gather() first.  The next
+// iteration's γ, boundary and opacity kernels (which do not read S) run under it.
+static int exchange_S_deferred(vrt_solver* s) {
+    if (!s->comm || getenv("VRT_NO_DEFERRED_GATHER")) return exchange(s, s->S.p, s->n_pad * s->nlam, 4);
+    cudaStream_t cs = comm_stream(s->comm);
+    for (auto& e : s->comm_ev)
+        if (!e) VRT_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    if (!s->gather_ev) VRT_CUDA(cudaEventCreateWithFlags(&s->gather_ev, cudaEventDisableTiming));
+    VRT_CUDA(cudaEventRecord(s->comm_ev[0], 0));
+    VRT_CUDA(cudaStreamWaitEvent(cs, s->comm_ev[0], 0));
+    VRT_TRY(comm_op(s->comm, s->S.p, s->n_pad * s->nlam, 4, cs));
+    VRT_CUDA(cudaEventRecord(s->gather_ev, cs));
+    s->gather_pending = true;
+    return VRT_OK;
+}
+static int wait_gather(vrt_solver* s) {
+    if (s->gather_pending) {
+        VRT_CUDA(cudaStreamWaitEvent(0, s->gather_ev, 0));
+        s->gather_pending = false;
+    }
+    return VRT_OK;
+}
+
 // J_λ_voronoi on device state: s->S -> s->J (internal order)
 // scatter: false = all-reduce J over the direction shards (every rank gets the full J); true = reduce-scatter over cells
 static int mean_intensity_internal(vrt_solver* s, SweepStats* stats, double* t_opacity_ms, double* t_sweep_ms, bool scatter = false) {
@@ -862,6 +889,7 @@ static int mean_intensity_internal(vrt_solver* s, SweepStats* stats, double* t_o
                 stats->kernels += 1;
             }
             VRT_CUDA(cudaGetLastError());
+            VRT_TRY(wait_gather(s));   // the sweep reads S of every cell
             VRT_TRY(sweep_run(s->g, nb, dirs.data(), s->S.p + l0, s->nlam, lc, 0, stats));
             k_J_reduce<<<nblocks(n * lc, 256), 256>>>(n, lc, jd, s->J.p + l0, s->nlam, d0 == 0);
             stats->kernels += 1;
@@ -965,6 +993,7 @@ static int set_field(vrt_solver* s, int field, const double* data) {
 }
 
 static int ensure_state(vrt_solver* s) {
+    VRT_TRY(wait_gather(s));   // every entry point that reads or writes the state passes here
     if (s->have_state) return VRT_OK;
     const int64_t n = s->n;
     if (s->is_line && !s->lte.p) {
@@ -1209,6 +1238,7 @@ int vrt_mean_intensity(vrt_solver* s, const double* S, const double* populations
     }
     const int64_t n = s->n;
     SweepStats stats;
+    VRT_TRY(wait_gather(s));
     VRT_TRY(upload_rows(s->g, S, s->S.p, s->nlam, s->stage));
     stats.kernels += 1;
     if (s->is_line) {
@@ -1346,7 +1376,6 @@ int vrt_lambda_iterate(vrt_solver* s, double eps, int32_t maxiter, vrt_iter_cb c
             k_pack_pops<<<nblocks(s->cs, 256), 256>>>(n, s->cs * s->cell_r, s->cs, s->pops.p, s->pops_blk.p + (size_t)3 * s->cs * s->cell_r);
             VRT_CUDA(cudaGetLastError());
             VRT_TRY(exchange(s, s->pops_blk.p, 3 * s->n_pad, 4));
-            VRT_TRY(exchange(s, s->S.p, s->n_pad * s->nlam, 4));
             k_unpack_pops<<<nblocks(n, 256), 256>>>(n, s->cs, s->cell_R, s->pops_blk.p, s->pops.p);
             stats.kernels += 2;
         }
@@ -1362,6 +1391,9 @@ int vrt_lambda_iterate(vrt_solver* s, double eps, int32_t maxiter, vrt_iter_cb c
             info.t_stateq_ms = ms;
         }
         VRT_TRY(read_diff(s, &diff));
+        // S of the other ranks' cells: after the criterion's reduction on the collectives' stream, so that the host does not
+        // wait for it; the next sweep does (wait_gather)
+        if (cshard) VRT_TRY(exchange_S_deferred(s));
         i++;
         info.iteration = i;
         info.updates = (double)n * s->nd * (double)s->nlam;
@@ -1369,6 +1401,7 @@ int vrt_lambda_iterate(vrt_solver* s, double eps, int32_t maxiter, vrt_iter_cb c
         total.kernels += stats.kernels; total.visits += stats.visits; total.steps += stats.steps; total.sweep_ms += stats.sweep_ms;
         if (cb && cb(&info, user) != 0) break;
     }
+    VRT_TRY(wait_gather(s));
     g_last_stats = total;
     if (out) {
         out->iterations = i;
