@@ -477,6 +477,7 @@ struct vrt_solver {
     std::vector<int> qdown;
     std::vector<std::array<double, 3>> qk;
     std::vector<DirSchedule*> sch;
+    std::vector<int> order;                 // order the directions are swept in (batches of `db` consecutive entries)
     int64_t n1_up = 0, n1_dn = 0;
     // per-site device arrays, internal order
     DevBuf<double> T, ne, NH, vz, vx, vy, dD, alpha_cont, eps, B0, Cp, lte, lam_dev, gamma;
@@ -593,6 +594,20 @@ static int solver_common_init(vrt_solver* s, vrt_grid* g, const vrt_quadrature* 
         s->sch.push_back(sc);
     }
     s->nd = (int)s->qk.size();
+    // Directions in flight together share the S rows they read when they walk through the grid side by side: the batches
+    // are therefore formed from directions of the same sense (up / down) and neighbouring inclination.  J then adds the
+    // directions in this order instead of the order of the quadrature file (rounding-level difference; VRT_DIR_ORDER=0
+    // keeps the file order).
+    s->order.resize(s->nd);
+    for (int d = 0; d < s->nd; d++) s->order[d] = d;
+    {
+        const char* e = getenv("VRT_DIR_ORDER");
+        if (e && atoi(e) == 1 && !g->regular)
+            std::stable_sort(s->order.begin(), s->order.end(), [&](int a, int b) {
+                if (s->qdown[a] != s->qdown[b]) return s->qdown[a] < s->qdown[b];
+                return fabs(s->qk[a][0]) > fabs(s->qk[b][0]);      // steep rays first
+            });
+    }
     s->n1_up = g->off_up[1] - 1;
     s->n1_dn = g->off_down[1] - 1;
     if (g->regular && s->cell_R > 1) {
@@ -691,8 +706,8 @@ static int plan_buffers(vrt_solver* s) {
     // buffer slot j serves directions j, j+db, ...: size for the largest of them
     for (int j = 0; j < db; j++) {
         int64_t scr[MAX_SWEEPS] = {0};
-        for (int d = j; d < s->nd; d += db)
-            for (int k = 0; k < MAX_SWEEPS; k++) scr[k] = std::max(scr[k], s->sch[d]->scr_rows[k]);
+        for (int q = j; q < s->nd; q += db)
+            for (int k = 0; k < MAX_SWEEPS; k++) scr[k] = std::max(scr[k], s->sch[s->order[q]]->scr_rows[k]);
         auto* bi = new DevBuf<double>();
         s->bufs.push_back(bi);
         VRT_TRY(bi->alloc((size_t)n * lc + 2));
@@ -851,7 +866,7 @@ static int mean_intensity_internal(vrt_solver* s, SweepStats* stats, double* t_o
             JDirs jd;
             od.nd = jd.nd = nb;
             for (int j = 0; j < nb; j++) {
-                int d = d0 + j;
+                int d = s->order[d0 + j];
                 dirs[j].sch = s->sch[d];
                 dirs[j].I_main = s->I_p[j];
                 dirs[j].alpha = s->is_line ? s->alpha_p[j] : s->alpha_cont.p;

@@ -44,6 +44,7 @@ struct SweepParams {
     int cv;                  // visits per chunk
     int32_t epoch;
     int32_t run_len;         // visits per producer run (<= 32)
+    int32_t pacing;          // 1: global round r runs step r*T_d/T of direction d (same relative progress); 0: step r
     int32_t experiment;      // VRT_EXPERIMENT: timing experiments only (0 in production)
     unsigned long long* prof; // experiment 2: per-role cycle counters
 };
@@ -232,9 +233,15 @@ __global__ void __launch_bounds__(SWEEP_BLOCK, SWEEP_MIN_BLOCKS) k_sweep(const S
     // producers' flags are (almost) always set by the time a chunk looks at them.
     const int G = P.T * P.nd;
     for (int g = 0; g < G; g++) {
-        const int d = g % P.nd, t = g / P.nd;
+        const int d = g % P.nd, r = g / P.nd;
         const DirDev* __restrict__ D = DT.d + d;
-        if (t >= D->nsteps) continue;
+        int t = r;
+        if (P.pacing) {   // proportional pacing: every direction advances through its program at the same relative speed
+            const long long Td = D->nsteps;
+            t = (int)(((long long)r * Td) / P.T);
+            if ((int)(((long long)(r + 1) * Td) / P.T) == t) continue;
+        } else if (t >= D->nsteps)
+            continue;
         const int beg = __ldg(D->step_off + t);
         const int total = (__ldg(D->step_off + t + 1) - beg) / cv;
         const Visit* __restrict__ visits = D->visits;
@@ -370,9 +377,15 @@ __global__ void __launch_bounds__(32 * (TMA_NP + TMA_NC), 3) k_sweep_tma(const S
         const int64_t ldS = P.ldS;
         const int G = P.T * P.nd;
         for (int g = 0; g < G; g++) {
-            const int d = g % P.nd, t = g / P.nd;
+            const int d = g % P.nd, r = g / P.nd;
             const DirDev* __restrict__ D = sdirs + d;
-            if (t >= D->nsteps) continue;
+            int t = r;
+            if (P.pacing) {   // proportional pacing: every direction advances through its program at the same relative speed
+                const long long Td = D->nsteps;
+                t = (int)(((long long)r * Td) / P.T);
+                if ((int)(((long long)(r + 1) * Td) / P.T) == t) continue;
+            } else if (t >= D->nsteps)
+                continue;
             const int dbeg = __ldg(D->step_off + t);
             const int dlen = __ldg(D->step_off + t + 1) - dbeg;
             const int total = (dlen + RL - 1) / RL;           // runs of this step
@@ -617,9 +630,15 @@ __global__ void __launch_bounds__(32 * (TMA_NP + TMA_NC), 3) k_sweep_dec(const S
         const int64_t ldS = P.ldS;
         const int G = P.T * P.nd;
         for (int g = 0; g < G; g++) {
-            const int d = g % P.nd, t = g / P.nd;
+            const int d = g % P.nd, r = g / P.nd;
             const DirDev* __restrict__ D = sdirs + d;
-            if (t >= D->nsteps) continue;
+            int t = r;
+            if (P.pacing) {   // proportional pacing: every direction advances through its program at the same relative speed
+                const long long Td = D->nsteps;
+                t = (int)(((long long)r * Td) / P.T);
+                if ((int)(((long long)(r + 1) * Td) / P.T) == t) continue;
+            } else if (t >= D->nsteps)
+                continue;
             const int dbeg = __ldg(D->step_off + t);
             const int dlen = __ldg(D->step_off + t + 1) - dbeg;
             const int total = (dlen + RL - 1) / RL;
@@ -885,6 +904,7 @@ int sweep_run(vrt_grid* g, int nd, const SweepDir* dirs, const double* S, int64_
     P.epoch = epoch;
     P.run_len = getenv("VRT_RUN_LEN") ? std::max(1, std::min(32, atoi(getenv("VRT_RUN_LEN")))) : 32;
     P.experiment = getenv("VRT_EXPERIMENT") ? atoi(getenv("VRT_EXPERIMENT")) : 0;
+    P.pacing = getenv("VRT_PACING") ? atoi(getenv("VRT_PACING")) : 0;
     P.prof = nullptr;
     DevBuf<unsigned long long> d_prof;
     if (P.experiment == 2) {
