@@ -232,20 +232,26 @@ def cpu_reference_sample(P, line, inputs, threads, target_updates=2.0e8, hoist=0
     from voronoirt_b200 import api, atom
     threads = O.set_num_threads(max(1, threads))
     lte, α_cont, ελ, Cr = inputs
-    atm = P["atm"]
-    b = P["bounds"]
-    bounds = [b["z_min"], b["z_max"], b["x_min"], b["x_max"], b["y_min"], b["y_max"]]
-    osites = O.Sites(np.ascontiguousarray(P["pos"].T), np.ascontiguousarray(P["nbr"].T), bounds)
-    sd = O.make_site_data(temperature=atm["temperature"], electron_density=atm["electron_density"], hydrogen_density=atm["hydrogen_density"],
-                          velocity_z=atm["velocity_z"], velocity_x=atm["velocity_x"], velocity_y=atm["velocity_y"], doppler_width=line.ΔD,
-                          alpha_cont=α_cont, destruction=ελ, C=np.ascontiguousarray(Cr.T), lte_pops=np.ascontiguousarray(lte.T))
+    ctx = P.get("_oracle_ctx")
+    if ctx is None:      # the oracle's grid (read_cell restated: layers, permutations, Delaunay lines) is built once per problem
+        atm = P["atm"]
+        b = P["bounds"]
+        bounds = [b["z_min"], b["z_max"], b["x_min"], b["x_max"], b["y_min"], b["y_max"]]
+        t0 = time.time()
+        osites = O.Sites(np.ascontiguousarray(P["pos"].T), np.ascontiguousarray(P["nbr"].T), bounds)
+        sd = O.make_site_data(temperature=atm["temperature"], electron_density=atm["electron_density"], hydrogen_density=atm["hydrogen_density"],
+                              velocity_z=atm["velocity_z"], velocity_x=atm["velocity_x"], velocity_y=atm["velocity_y"], doppler_width=line.ΔD,
+                              alpha_cont=α_cont, destruction=ελ, C=np.ascontiguousarray(Cr.T), lte_pops=np.ascontiguousarray(lte.T))
+        S = np.ascontiguousarray(atom.B_λ(line.λ[None, :], atm["temperature"][:, None]))
+        ctx = P["_oracle_ctx"] = (osites, sd, S)
+        log(f"CPU oracle: grid of {P['n']} sites built in {time.time() - t0:.1f}s")
+    osites, sd, S = ctx
     w, th, ph, nq = api.read_quadrature(P["qpath"])
     nlam = len(line.λ)
     nl = min(nlam, threads)
     kd = int(min(nq, max(1, round(target_updates / (P["n"] * nl)))))      # bounded sample: first kd directions of the table
     w, th, ph, nq = w[:kd], th[:kd], ph[:kd], kd
     oq = O.make_quadrature(w, th, ph)
-    S = np.ascontiguousarray(atom.B_λ(line.λ[None, :], atm["temperature"][:, None]))
     ls = line.as_struct()
     l0 = max(0, line.λidx[1] // 2 - nl // 2)
     box = {}

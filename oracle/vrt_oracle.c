@@ -96,6 +96,9 @@ int orc_sort_by_layer(const int64_t* nbr, int64_t n, int64_t wall, int64_t* laye
     int64_t lower = 1;
     for (;;) {
         int64_t assigned = 0;
+        /* a pass tests `== lower` and writes `lower + 1` only (voronoi_utils.jl:114): its result does not depend on the
+         * order of the sites, so the scan may run in parallel (set-up of the 16 M-site baseline would take minutes otherwise) */
+#pragma omp parallel for reduction(+ : assigned) schedule(static)
         for (int64_t i = 0; i < n; i++) {
             if (layers[i] == 0) {
                 int64_t cnt = nbr[i];
@@ -110,8 +113,9 @@ int orc_sort_by_layer(const int64_t* nbr, int64_t n, int64_t wall, int64_t* laye
             }
         }
         int any0 = 0;
+#pragma omp parallel for reduction(| : any0) schedule(static)
         for (int64_t i = 0; i < n; i++)
-            if (layers[i] == 0) { any0 = 1; break; }
+            if (layers[i] == 0) any0 |= 1;
         if (!any0) break;
         if (assigned == 0) return -1;
         lower++;
@@ -156,6 +160,7 @@ static int64_t orc_reduce_layers(const int64_t* sorted, int64_t n, int64_t* out)
  * src/voronoi_utils.jl:186-245, including the mirror quirk at :221-222/:231-232 (Q3). */
 static void orc_calc_delaunay_lines(orc_sites* s) {
     int64_t n = s->n, mnb = s->max_nb;
+#pragma omp parallel for schedule(static)
     for (int64_t i = 0; i < n; i++) {
         const double* P = s->pos + 3 * i;
         double x_r_r = s->x_max - P[1];
@@ -518,13 +523,16 @@ void orc_J_lambda_voronoi(const orc_sites* s, const vrt_line* line, const double
                           double* J, double* damping, int64_t l0, int64_t l1, int hoist) {
     int64_t n = s->n, nlam = line->nlam;
     if (l1 <= l0) { l0 = 0; l1 = nlam; }
-    for (int64_t i = 0; i < n * nlam; i++) J[i] = 0.0;
+    /* a wavelength sub-range [l0, l1) (bounded CPU-baseline sample) only touches its own columns of J and damping: the
+     * sample then carries its own share of this per-call work, not that of all nlam wavelengths */
+    for (int64_t i = 0; i < n; i++)
+        for (int64_t l = l0; l < l1; l++) J[l + nlam * i] = 0.0;
     double* gamma = (double*)malloc(sizeof(double) * (size_t)n);
     double* nHI = (double*)malloc(sizeof(double) * (size_t)n);
     for (int64_t i = 0; i < n; i++) nHI[i] = pops[i] + pops[i + n];
     orc_gamma_constant(line, n, sd->temperature, nHI, sd->electron_density, gamma);
     for (int64_t i = 0; i < n; i++)
-        for (int64_t l = 0; l < nlam; l++) damping[l + nlam * i] = orc_damping(gamma[i], lambda[l], sd->doppler_width[i]);
+        for (int64_t l = l0; l < l1; l++) damping[l + nlam * i] = orc_damping(gamma[i], lambda[l], sd->doppler_width[i]);
     double* vlos = (double*)malloc(sizeof(double) * (size_t)n);
     int64_t* st_up = NULL; double *st_w = NULL, *st_r = NULL;
     if (hoist) {

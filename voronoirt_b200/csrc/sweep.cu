@@ -44,6 +44,7 @@ struct SweepParams {
     int cv;                  // visits per chunk
     int32_t epoch;
     int32_t run_len;         // visits per producer run (<= 32)
+    int32_t pf_lead;         // >= 0: L2 prefetch of a visit's rows once it is within ns + pf_lead chunks of the ring's tail; < 0: off
     int32_t pacing;          // 1: global round r runs step r*T_d/T of direction d (same relative progress); 0: step r
     int32_t experiment;      // VRT_EXPERIMENT: timing experiments only (0 in production)
     unsigned long long* prof; // experiment 2: per-role cycle counters
@@ -328,6 +329,11 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint3
 }
 
 
+// brings a row into L2 without occupying shared memory (the stage ring bounds the bytes in flight; this does not)
+__device__ __forceinline__ void bulk_prefetch_l2(const void* gsrc, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gsrc), "r"(bytes) : "memory");
+}
+
 constexpr int TMA_MAX_STAGES = 32;
 #ifndef TMA_DEFER
 #define TMA_DEFER 12
@@ -400,6 +406,34 @@ __global__ void __launch_bounds__(32 * (TMA_NP + TMA_NC), 3) k_sweep_tma(const S
                     const unsigned my = it + (unsigned)lane;
                     const int stage = (int)(my % (unsigned)ns);
                     const uint32_t round = my / (unsigned)ns;
+                    if (P.pf_lead >= 0) {
+                        // L2 prefetch of the visit's eight rows while the lane still waits for its ring stage: the bulk copies
+                        // issued later then find their rows in L2, so a stage is in flight for an L2 round trip instead of a
+                        // DRAM one.  The lead is bounded (ns + pf_lead chunks per CTA) so that what is prefetched is still in
+                        // L2 when it is used.  Rows written later in this launch (upwind intensities not yet computed) are
+                        // harmless to prefetch: L2 is the point of coherence, the producer's store updates the line in place.
+                        const long long q = (long long)my - ns - P.pf_lead;
+                        if (q >= 0) {
+                            const int qs = (int)(q % ns);
+                            const uint32_t qr = (uint32_t)(q / ns) + 1u;
+                            while ((int32_t)(consumed[qs] - qr) < 0) __nanosleep(100);
+                        }
+                        const uint32_t nbp = (uint32_t)(((nlam + 1) * 8 + 15) & ~15);
+                        const double* alpha_ = D->alpha;
+                        const double* S_ = P.S;
+                        const uintptr_t m16 = ~(uintptr_t)15;
+                        bulk_prefetch_l2(reinterpret_cast<const void*>(reinterpret_cast<uintptr_t>(alpha_ + (size_t)v.a.x * nlam) & m16), nbp);
+                        bulk_prefetch_l2(reinterpret_cast<const void*>(reinterpret_cast<uintptr_t>(S_ + (size_t)v.a.x * P.ldS) & m16), nbp);
+                        bulk_prefetch_l2(reinterpret_cast<const void*>(reinterpret_cast<uintptr_t>(alpha_ + (size_t)v.a.z * nlam) & m16), nbp);
+                        bulk_prefetch_l2(reinterpret_cast<const void*>(reinterpret_cast<uintptr_t>(S_ + (size_t)v.a.z * P.ldS) & m16), nbp);
+                        bulk_prefetch_l2(reinterpret_cast<const void*>(reinterpret_cast<uintptr_t>(alpha_ + (size_t)v.a.w * nlam) & m16), nbp);
+                        bulk_prefetch_l2(reinterpret_cast<const void*>(reinterpret_cast<uintptr_t>(S_ + (size_t)v.a.w * P.ldS) & m16), nbp);
+                        const uint32_t s1 = v.b.x >> SEL_SHIFT, s2 = v.b.y >> SEL_SHIFT;
+                        if (s1 != SEL_ZERO)
+                            bulk_prefetch_l2(reinterpret_cast<const void*>(reinterpret_cast<uintptr_t>((s1 == SEL_MAIN ? D->I_main : D->scratch[s1 - SEL_SCR0]) + (size_t)(v.b.x & ROW_MASK) * nlam) & m16), nbp);
+                        if (s2 != SEL_ZERO)
+                            bulk_prefetch_l2(reinterpret_cast<const void*>(reinterpret_cast<uintptr_t>((s2 == SEL_MAIN ? D->I_main : D->scratch[s2 - SEL_SCR0]) + (size_t)(v.b.y & ROW_MASK) * nlam) & m16), nbp);
+                    }
                     wait_flags2(D->flags, v.b.z, v.b.w, epoch, P.experiment != 4);   // ends with an acquire fence (generic proxy; experiment 4 times its cost)
                     asm volatile("fence.proxy.async;" ::: "memory");   // ... which the bulk copies (async proxy) are ordered after
                     // rows of the stage: 0 α_c, 1 S_c, 2 α_u1, 3 S_u1, 4 I_u1, 5 α_u2, 6 S_u2, 7 I_u2
@@ -905,6 +939,7 @@ int sweep_run(vrt_grid* g, int nd, const SweepDir* dirs, const double* S, int64_
     P.run_len = getenv("VRT_RUN_LEN") ? std::max(1, std::min(32, atoi(getenv("VRT_RUN_LEN")))) : 32;
     P.experiment = getenv("VRT_EXPERIMENT") ? atoi(getenv("VRT_EXPERIMENT")) : 0;
     P.pacing = getenv("VRT_PACING") ? atoi(getenv("VRT_PACING")) : 0;
+    P.pf_lead = getenv("VRT_PF_LEAD") ? atoi(getenv("VRT_PF_LEAD")) : -1;
     P.prof = nullptr;
     DevBuf<unsigned long long> d_prof;
     if (P.experiment == 2) {
