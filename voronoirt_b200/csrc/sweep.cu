@@ -44,7 +44,6 @@ struct SweepParams {
     int cv;                  // visits per chunk
     int32_t epoch;
     int32_t run_len;         // visits per producer run (<= 32)
-    int32_t pf_lead;         // >= 0: L2 prefetch of a visit's rows once it is within ns + pf_lead chunks of the ring's tail; < 0: off
     int32_t pacing;          // 1: global round r runs step r*T_d/T of direction d (same relative progress); 0: step r
     int32_t experiment;      // VRT_EXPERIMENT: timing experiments only (0 in production)
     unsigned long long* prof; // experiment 2: per-role cycle counters
@@ -329,11 +328,6 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint3
 }
 
 
-// brings a row into L2 without occupying shared memory (the stage ring bounds the bytes in flight; this does not)
-__device__ __forceinline__ void bulk_prefetch_l2(const void* gsrc, uint32_t bytes) {
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gsrc), "r"(bytes) : "memory");
-}
-
 constexpr int TMA_MAX_STAGES = 32;
 #ifndef TMA_DEFER
 #define TMA_DEFER 12
@@ -406,34 +400,6 @@ __global__ void __launch_bounds__(32 * (TMA_NP + TMA_NC), 3) k_sweep_tma(const S
                     const unsigned my = it + (unsigned)lane;
                     const int stage = (int)(my % (unsigned)ns);
                     const uint32_t round = my / (unsigned)ns;
-                    if (P.pf_lead >= 0) {
-                        // L2 prefetch of the visit's eight rows while the lane still waits for its ring stage: the bulk copies
-                        // issued later then find their rows in L2, so a stage is in flight for an L2 round trip instead of a
-                        // DRAM one.  The lead is bounded (ns + pf_lead chunks per CTA) so that what is prefetched is still in
-                        // L2 when it is used.  Rows written later in this launch (upwind intensities not yet computed) are
-                        // harmless to prefetch: L2 is the point of coherence, the producer's store updates the line in place.
-                        const long long q = (long long)my - ns - P.pf_lead;
-                        if (q >= 0) {
-                            const int qs = (int)(q % ns);
-                            const uint32_t qr = (uint32_t)(q / ns) + 1u;
-                            while ((int32_t)(consumed[qs] - qr) < 0) __nanosleep(100);
-                        }
-                        const uint32_t nbp = (uint32_t)(((nlam + 1) * 8 + 15) & ~15);
-                        const double* alpha_ = D->alpha;
-                        const double* S_ = P.S;
-                        const uintptr_t m16 = ~(uintptr_t)15;
-                        bulk_prefetch_l2(reinterpret_cast<const void*>(reinterpret_cast<uintptr_t>(alpha_ + (size_t)v.a.x * nlam) & m16), nbp);
-                        bulk_prefetch_l2(reinterpret_cast<const void*>(reinterpret_cast<uintptr_t>(S_ + (size_t)v.a.x * P.ldS) & m16), nbp);
-                        bulk_prefetch_l2(reinterpret_cast<const void*>(reinterpret_cast<uintptr_t>(alpha_ + (size_t)v.a.z * nlam) & m16), nbp);
-                        bulk_prefetch_l2(reinterpret_cast<const void*>(reinterpret_cast<uintptr_t>(S_ + (size_t)v.a.z * P.ldS) & m16), nbp);
-                        bulk_prefetch_l2(reinterpret_cast<const void*>(reinterpret_cast<uintptr_t>(alpha_ + (size_t)v.a.w * nlam) & m16), nbp);
-                        bulk_prefetch_l2(reinterpret_cast<const void*>(reinterpret_cast<uintptr_t>(S_ + (size_t)v.a.w * P.ldS) & m16), nbp);
-                        const uint32_t s1 = v.b.x >> SEL_SHIFT, s2 = v.b.y >> SEL_SHIFT;
-                        if (s1 != SEL_ZERO)
-                            bulk_prefetch_l2(reinterpret_cast<const void*>(reinterpret_cast<uintptr_t>((s1 == SEL_MAIN ? D->I_main : D->scratch[s1 - SEL_SCR0]) + (size_t)(v.b.x & ROW_MASK) * nlam) & m16), nbp);
-                        if (s2 != SEL_ZERO)
-                            bulk_prefetch_l2(reinterpret_cast<const void*>(reinterpret_cast<uintptr_t>((s2 == SEL_MAIN ? D->I_main : D->scratch[s2 - SEL_SCR0]) + (size_t)(v.b.y & ROW_MASK) * nlam) & m16), nbp);
-                    }
                     wait_flags2(D->flags, v.b.z, v.b.w, epoch, P.experiment != 4);   // ends with an acquire fence (generic proxy; experiment 4 times its cost)
                     asm volatile("fence.proxy.async;" ::: "memory");   // ... which the bulk copies (async proxy) are ordered after
                     // rows of the stage: 0 α_c, 1 S_c, 2 α_u1, 3 S_u1, 4 I_u1, 5 α_u2, 6 S_u2, 7 I_u2
@@ -604,241 +570,6 @@ __global__ void __launch_bounds__(32 * (TMA_NP + TMA_NC), 3) k_sweep_tma(const S
     }
 }
 
-// ---------------------------------------------------------------- decoupled variant (wide rows)
-// The stage ring of k_sweep_tma is gated by the dependencies: a producer lane waits for the two ready-flags of its visit
-// before it may issue the copies, because two of the eight rows (the upwind intensities) are written earlier in the same
-// launch.  Here the ring only carries what does NOT depend on the launch's own results — α_c S_c | α_u1 S_u1 | α_u2 S_u2 —
-// so the producers never look at a flag and run as far ahead as the ring allows, whatever the dependency structure of the
-// visit order.  The consumer warp that takes a stage polls the two flags itself (its data is already in shared memory),
-// then gathers the two intensity rows straight from L2 / HBM into registers (coalesced 256-byte loads per instruction).
-// A stage is 6 rows instead of 8 (a third more stages in the same shared memory); the price is the latency of the
-// intensity loads inside the consumer, hidden by the other consumer warps of the SM.
-struct __align__(16) StageHdrD {
-    double* dst;
-    int32_t* flag;
-    double w1, w2, hr1, hr2;
-    const double* i1;     // upwind intensity rows (nullptr: zero)
-    const double* i2;
-    const int32_t* f1;    // ready-flags of the chunks that produce them (nullptr: no producer)
-    const int32_t* f2;
-    uint32_t offs;        // bit r: row r starts one double into its 16-byte aligned copy
-    uint32_t valid;
-    uint32_t seq;
-    uint32_t pad;
-};
-static_assert(sizeof(StageHdrD) == 96, "StageHdrD must be 96 bytes");
-
-template <int TMA_NP, int TMA_NC>
-__global__ void __launch_bounds__(32 * (TMA_NP + TMA_NC), 3) k_sweep_dec(const SweepParams P, const __grid_constant__ DirTable DT, int ns, int rowb) {
-    extern __shared__ __align__(128) unsigned char smem[];
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem);
-    volatile uint32_t* consumed = reinterpret_cast<volatile uint32_t*>(full + TMA_MAX_STAGES);
-    unsigned int* next_chunk = const_cast<unsigned int*>(reinterpret_cast<volatile unsigned int*>(consumed + TMA_MAX_STAGES));
-    StageHdrD* hdr = reinterpret_cast<StageHdrD*>(smem + 2 * TMA_MAX_STAGES * sizeof(uint64_t));
-    DirDev* sdirs = reinterpret_cast<DirDev*>(smem + 2 * TMA_MAX_STAGES * sizeof(uint64_t) + TMA_MAX_STAGES * sizeof(StageHdrD));
-    unsigned char* data = smem + 2 * TMA_MAX_STAGES * sizeof(uint64_t) + TMA_MAX_STAGES * sizeof(StageHdrD) + MAX_DIRS * sizeof(DirDev);
-    const int lane = threadIdx.x & 31;
-    const int warp = threadIdx.x >> 5;
-    const int nlam = P.nlam;
-    const int32_t epoch = P.epoch;
-    for (int i = threadIdx.x; i < P.nd * (int)(sizeof(DirDev) / 8); i += blockDim.x)
-        reinterpret_cast<unsigned long long*>(sdirs)[i] = reinterpret_cast<const unsigned long long*>(DT.d)[i];
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < ns; s++) {
-            mbar_init(full + s, 1);
-            consumed[s] = 0;
-            if (s == 0) *next_chunk = 0;
-            hdr[s].seq = 0xffffffffu;
-        }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    if (warp < TMA_NP) {
-        // ===== producers: one visit per lane, no dependency in sight =====
-        long long rnext = blockIdx.x;
-        long long rbase = 0;
-        const long long nblk = gridDim.x;
-        unsigned it = 0, rc = 0;
-        const int RL = P.run_len;
-        const double* __restrict__ S = P.S;
-        const int64_t ldS = P.ldS;
-        const int G = P.T * P.nd;
-        for (int g = 0; g < G; g++) {
-            const int d = g % P.nd, r = g / P.nd;
-            const DirDev* __restrict__ D = sdirs + d;
-            int t = r;
-            if (P.pacing) {   // proportional pacing: every direction advances through its program at the same relative speed
-                const long long Td = D->nsteps;
-                t = (int)(((long long)r * Td) / P.T);
-                if ((int)(((long long)(r + 1) * Td) / P.T) == t) continue;
-            } else if (t >= D->nsteps)
-                continue;
-            const int dbeg = __ldg(D->step_off + t);
-            const int dlen = __ldg(D->step_off + t + 1) - dbeg;
-            const int total = (dlen + RL - 1) / RL;
-            while (rnext < rbase + total) {
-                const int first = (int)(rnext - rbase) * RL;
-                const int nrun = min(RL, dlen - first);
-                if (lane < nrun && (int)(rc % TMA_NP) == warp) {
-                    const int cj = dbeg + first + lane;
-                    const VisitRegs v = load_visit(D->visits + cj);
-                    const unsigned my = it + (unsigned)lane;
-                    const int stage = (int)(my % (unsigned)ns);
-                    const uint32_t round = my / (unsigned)ns;
-                    // rows of the stage: 0 α_c, 1 S_c, 2 α_u1, 3 S_u1, 4 α_u2, 5 S_u2
-                    const double* src[6];
-                    const double* alpha = D->alpha;
-                    src[0] = alpha + (size_t)v.a.x * nlam;
-                    src[1] = S + (size_t)v.a.x * ldS;
-                    src[2] = alpha + (size_t)v.a.z * nlam;
-                    src[3] = S + (size_t)v.a.z * ldS;
-                    src[4] = alpha + (size_t)v.a.w * nlam;
-                    src[5] = S + (size_t)v.a.w * ldS;
-                    uint32_t offmask = 0, tot = 0;
-#pragma unroll
-                    for (int r = 0; r < 6; r++) {
-                        const uint32_t off = (uint32_t)((reinterpret_cast<uintptr_t>(src[r]) >> 3) & 1u);
-                        offmask |= off << r;
-                        tot += (uint32_t)(((nlam + off) * 8 + 15) & ~15);
-                    }
-                    StageHdrD h;
-                    const uint32_t dsel = v.a.y >> SEL_SHIFT;
-                    h.dst = (dsel == SEL_MAIN ? D->I_main : D->scratch[dsel - SEL_SCR0]) + (size_t)(v.a.y & ROW_MASK) * nlam;
-                    h.flag = D->flags + cj;
-                    h.w1 = v.w.x; h.w2 = v.w.y; h.hr1 = v.hr.x; h.hr2 = v.hr.y;
-                    {
-                        const uint32_t s1 = v.b.x >> SEL_SHIFT, s2 = v.b.y >> SEL_SHIFT;
-                        h.i1 = s1 == SEL_ZERO ? nullptr : (s1 == SEL_MAIN ? D->I_main : D->scratch[s1 - SEL_SCR0]) + (size_t)(v.b.x & ROW_MASK) * nlam;
-                        h.i2 = s2 == SEL_ZERO ? nullptr : (s2 == SEL_MAIN ? D->I_main : D->scratch[s2 - SEL_SCR0]) + (size_t)(v.b.y & ROW_MASK) * nlam;
-                    }
-                    h.f1 = v.b.z == DEP_NONE ? nullptr : D->flags + v.b.z;
-                    h.f2 = v.b.w == DEP_NONE ? nullptr : D->flags + v.b.w;
-                    h.offs = offmask;
-                    h.valid = 1;
-                    h.seq = my;
-                    h.pad = 0;
-                    while (consumed[stage] != round) __nanosleep(100);
-                    __threadfence_block();
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                    hdr[stage] = h;
-                    mbar_arrive_expect_tx(full + stage, tot);
-#pragma unroll
-                    for (int r = 0; r < 6; r++) {
-                        const uint32_t off = (offmask >> r) & 1u;
-                        const uint32_t nb = (uint32_t)(((nlam + off) * 8 + 15) & ~15);
-                        bulk_g2s(data + (size_t)(stage * 6 + r) * rowb, src[r] - off, nb, full + stage);
-                    }
-                }
-                __syncwarp();
-                it += (unsigned)nrun;
-                rc++;
-                rnext += nblk;
-            }
-            rbase += total;
-        }
-        for (int k = 0; k < TMA_NC && warp == 0; k++) {
-            const int stage = (int)(it % (unsigned)ns);
-            if (lane == 0) {
-                while (consumed[stage] != it / (unsigned)ns) __nanosleep(32);
-                __threadfence_block();
-                hdr[stage].valid = 0;
-                hdr[stage].seq = it;
-                mbar_arrive(full + stage);
-            }
-            __syncwarp();
-            it++;
-        }
-    } else {
-        // ===== consumers =====
-        int32_t* pend[TMA_DEFER];
-        int np = 0;
-        for (;;) {
-            unsigned it = 0;
-            if (lane == 0) it = atomicAdd(next_chunk, 1u);
-            it = __shfl_sync(0xffffffffu, it, 0);
-            const int stage = (int)(it % (unsigned)ns);
-            const uint32_t par = (it / (unsigned)ns) & 1u;
-            bool ready = mbar_test(full + stage, par) && reinterpret_cast<volatile StageHdrD*>(hdr)[stage].seq == it;
-            if (!ready) {
-                if (np) {
-                    __syncwarp();
-                    if (lane == 0) set_flags(pend, np, epoch);
-                    np = 0;
-                }
-                for (;;) {
-                    mbar_wait(full + stage, par);
-                    if (reinterpret_cast<volatile StageHdrD*>(hdr)[stage].seq == it) break;
-                    __nanosleep(64);
-                }
-            }
-            const StageHdrD h = hdr[stage];
-            if (!h.valid) break;
-            // the two producers of this visit: a consumer never blocks while it holds unpublished flags (they may be what
-            // the chunk it waits for needs)
-            if (h.f1 || h.f2) {
-                const int32_t* f1 = h.f1 ? h.f1 : h.f2;
-                const int32_t* f2 = h.f2 ? h.f2 : h.f1;
-                int v1, v2;
-                asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v1) : "l"(f1) : "memory");
-                asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v2) : "l"(f2) : "memory");
-                if (v1 != epoch || v2 != epoch) {
-                    if (np) {
-                        __syncwarp();
-                        if (lane == 0) set_flags(pend, np, epoch);
-                        np = 0;
-                    }
-                    do {
-                        __nanosleep(100);
-                        asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v1) : "l"(f1) : "memory");
-                        asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v2) : "l"(f2) : "memory");
-                    } while (v1 != epoch || v2 != epoch);
-                }
-                asm volatile("fence.acq_rel.gpu;" ::: "memory");   // acquire: the producers' result rows are visible to the loads below
-            }
-            const unsigned char* rb = data + (size_t)stage * 6 * rowb;
-            const double* r0 = reinterpret_cast<const double*>(rb) + (h.offs & 1u) + lane;
-            const double* r1 = reinterpret_cast<const double*>(rb + rowb) + ((h.offs >> 1) & 1u) + lane;
-            const double* r2 = reinterpret_cast<const double*>(rb + 2 * rowb) + ((h.offs >> 2) & 1u) + lane;
-            const double* r3 = reinterpret_cast<const double*>(rb + 3 * rowb) + ((h.offs >> 3) & 1u) + lane;
-            const double* r5 = reinterpret_cast<const double*>(rb + 4 * rowb) + ((h.offs >> 4) & 1u) + lane;
-            const double* r6 = reinterpret_cast<const double*>(rb + 5 * rowb) + ((h.offs >> 5) & 1u) + lane;
-            const double* i1 = h.i1 ? h.i1 + lane : nullptr;
-            const double* i2 = h.i2 ? h.i2 + lane : nullptr;
-            double* out = h.dst + lane;
-            // the intensity loads of the first rounds are issued before any math (rows of up to 96 wavelengths in three rounds)
-            double I1a = 0.0, I2a = 0.0, I1b = 0.0, I2b = 0.0, I1c = 0.0, I2c = 0.0;
-            if (lane < nlam) { if (i1) I1a = __ldcg(i1); if (i2) I2a = __ldcg(i2); }
-            if (lane + 32 < nlam) { if (i1) I1b = __ldcg(i1 + 32); if (i2) I2b = __ldcg(i2 + 32); }
-            if (lane + 64 < nlam) { if (i1) I1c = __ldcg(i1 + 64); if (i2) I2c = __ldcg(i2 + 64); }
-            auto item = [&](int o, double I_1, double I_2) {
-                const double a_c = r0[o], S_c = r1[o];
-                double a, b, e;
-                linear_weights(h.hr1 * (a_c + r2[o]), a, b, e);
-                double I = 0.0 + (e * I_1 + a * r3[o] + b * S_c) * h.w1;
-                linear_weights(h.hr2 * (a_c + r5[o]), a, b, e);
-                I += (e * I_2 + a * r6[o] + b * S_c) * h.w2;
-                out[o] = I;
-            };
-            if (lane < nlam) item(0, I1a, I2a);
-            if (lane + 32 < nlam) item(32, I1b, I2b);
-            if (lane + 64 < nlam) item(64, I1c, I2c);
-            for (int o = 96; lane + o < nlam; o += 32) item(o, i1 ? __ldcg(i1 + o) : 0.0, i2 ? __ldcg(i2 + o) : 0.0);
-            __syncwarp();
-            if (lane == 0) {
-                __threadfence_block();
-                consumed[stage] = it / (unsigned)ns + 1u;
-            }
-            pend[np++] = h.flag;
-            if (np == TMA_DEFER) {
-                if (lane == 0) set_flags(pend, TMA_DEFER, epoch);
-                np = 0;
-            }
-        }
-        __syncwarp();
-        if (lane == 0) set_flags(pend, np, epoch);
-    }
-}
-
 // events of the launches since the last sweep_collect(): (start, stop) pairs from a pool owned by the grid
 struct SweepTimers {
     std::vector<cudaEvent_t> pool;   // 2 per launch
@@ -939,7 +670,6 @@ int sweep_run(vrt_grid* g, int nd, const SweepDir* dirs, const double* S, int64_
     P.run_len = getenv("VRT_RUN_LEN") ? std::max(1, std::min(32, atoi(getenv("VRT_RUN_LEN")))) : 32;
     P.experiment = getenv("VRT_EXPERIMENT") ? atoi(getenv("VRT_EXPERIMENT")) : 0;
     P.pacing = getenv("VRT_PACING") ? atoi(getenv("VRT_PACING")) : 0;
-    P.pf_lead = getenv("VRT_PF_LEAD") ? atoi(getenv("VRT_PF_LEAD")) : -1;
     P.prof = nullptr;
     DevBuf<unsigned long long> d_prof;
     if (P.experiment == 2) {
@@ -957,29 +687,7 @@ int sweep_run(vrt_grid* g, int nd, const SweepDir* dirs, const double* S, int64_
     const void* fn = nullptr;
     int block = 0, ns = 0, rowb = 0;
     size_t shmem = 0;
-    const char* env_dec = getenv("VRT_SWEEP_DECOUPLED");
-    const bool decoupled = env_dec ? atoi(env_dec) != 0 : false;
-    if (use_tma && decoupled) {
-        const char* env_cfg = getenv("VRT_TMA_CFG");
-        const int cfg = env_cfg ? atoi(env_cfg) : 27;
-        switch (cfg) {
-            case 26: fn = (const void*)k_sweep_dec<2, 6>; block = 32 * 8; break;
-            case 17: fn = (const void*)k_sweep_dec<1, 7>; block = 32 * 8; break;
-            case 18: fn = (const void*)k_sweep_dec<1, 8>; block = 32 * 9; break;
-            default: fn = (const void*)k_sweep_dec<2, 7>; block = 32 * 9; break;
-        }
-        rowb = (int)(((nlam + 1) * 8 + 15) & ~15);
-        const size_t fixed = 2 * TMA_MAX_STAGES * sizeof(uint64_t) + TMA_MAX_STAGES * sizeof(StageHdrD) + MAX_DIRS * sizeof(DirDev);
-        const char* env_ns = getenv("VRT_TMA_STAGES");
-        const char* env_kb = getenv("VRT_TMA_SMEM_KB");
-        const size_t budget = (size_t)(env_kb && atoi(env_kb) > 0 ? atoi(env_kb) : 72) * 1024;
-        ns = (int)((budget - fixed) / ((size_t)6 * rowb));
-        if (env_ns && atoi(env_ns) > 0) ns = atoi(env_ns);
-        ns = std::max(2, std::min(ns, TMA_MAX_STAGES));
-        shmem = fixed + (size_t)ns * 6 * rowb;
-        if (shmem > (size_t)smem_max) use_tma = false;
-        else VRT_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
-    } else if (use_tma) {
+    if (use_tma) {
         const char* env_cfg = getenv("VRT_TMA_CFG");
         const int cfg = env_cfg ? atoi(env_cfg) : 27;
         switch (cfg) {
