@@ -169,7 +169,9 @@ def _gloo_worker(rank, world, port, q):
     Jm[:, lo:hi] = J[:, lo:hi]
     tJ = torch.from_numpy(Jm)
     dist.all_reduce(tJ)                               # emulates "J is owner-complete per wavelength"
-    R = O.calculate_R(line.as_struct(), line.λ, a["temperature"], line.ΔD, tJ.numpy(), damping, lte.T)
+    tD = torch.from_numpy(damping)                    # a shard only fills its own columns of the damping parameter, too
+    dist.all_reduce(tD)
+    R = O.calculate_R(line.as_struct(), line.λ, a["temperature"], line.ΔD, tJ.numpy(), tD.numpy(), lte.T)
     diff_local = torch.tensor([float(np.abs(J[:, lo:hi]).max())], dtype=torch.float64)
     dist.all_reduce(diff_local, op=dist.ReduceOp.MAX)
     if rank == 0:
