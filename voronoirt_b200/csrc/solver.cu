@@ -124,11 +124,6 @@ struct OpacityDirs {
     int nd;
 };
 
-struct JDirs {
-    const double* I[MAX_DIRS];
-    double w[MAX_DIRS];
-    int nd;
-};
 // compute_voigt_profile (line.jl:121-137) + αline_λ (line.jl:219-225) + α_cont, for every direction of the batch.
 // A CTA owns a tile of OP_TC cells x all lc wavelengths.  The math runs with the 32 lanes of a warp on 32 DIFFERENT
 // CELLS at the SAME wavelength: the Humlíček region (|v| + a) is then almost warp-uniform, whereas lanes over
@@ -143,8 +138,7 @@ __global__ void __launch_bounds__(OP_THREADS) k_opacity(int64_t n, int64_t lc, c
                                                         const OpacityDirs D, const double* __restrict__ gamma,
                                                         const double* __restrict__ dD, const double* __restrict__ vz,
                                                         const double* __restrict__ vx, const double* __restrict__ vy,
-                                                        const double* __restrict__ pops, const double* __restrict__ alpha_cont,
-                                                        const JDirs JA, double* __restrict__ Jout, int64_t ldJ, int jfirst) {
+                                                        const double* __restrict__ pops, const double* __restrict__ alpha_cont) {
     extern __shared__ double tile[];                 // [OP_TC][ldt] α of one direction, then [OP_TC][ldt] damping a
     const int ldt = (int)lc | 1;                     // odd row stride: conflict-light transposed writes
     double* atile = tile + OP_TC * ldt;
@@ -159,19 +153,6 @@ __global__ void __launch_bounds__(OP_THREADS) k_opacity(int64_t n, int64_t lc, c
         const double ac = alpha_cont[cc];
         const double v0 = vz[cc], v1 = vx[cc], v2 = vy[cc];
         const int ncell = (int)min((int64_t)OP_TC, n - c0);
-        // J += Σ w I of the PREVIOUS direction batch (lambda_iteration.jl:102,107), same order of additions as k_J_reduce:
-        // this kernel is fp64-bound and leaves most of the DRAM bandwidth idle, so the 4 rows per cell and batch that a
-        // separate pass would stream ride along for free (the intensity buffers are overwritten only after this kernel)
-        if (JA.nd > 0) {
-            const int total = ncell * (int)lc;
-            for (int i = threadIdx.x; i < total; i += OP_THREADS) {
-                const int r = i / (int)lc, l = i - r * (int)lc;
-                double* j = Jout + (c0 + r) * ldJ + l;
-                double acc = jfirst ? 0.0 : *j;
-                for (int d = 0; d < JA.nd; d++) acc += JA.w[d] * JA.I[d][c0 * lc + i];
-                *j = acc;
-            }
-        }
         // each thread fills and later reads its own entries of atile (same cell, same wavelengths): no barrier needed
         for (int l = warp; l < lc; l += nwarp) atile[lane * ldt + l] = damping_param(g, lam[l], dd);
         for (int d = 0; d < D.nd; d++) {
@@ -204,6 +185,11 @@ __global__ void k_damping(int64_t n, int64_t nlam, const double* __restrict__ la
 }
 
 // ---------------------------------------------------------------- J = Σ_Ω w_Ω I_Ω  (lambda_iteration.jl:102,107)
+struct JDirs {
+    const double* I[MAX_DIRS];
+    double w[MAX_DIRS];
+    int nd;
+};
 // atomics-free and deterministic: one thread owns (cell, λ) and adds the directions in quadrature-file order
 __global__ void k_J_reduce(int64_t n, int64_t lc, const JDirs D, double* __restrict__ J, int64_t ldJ, int first) {
     int64_t total = n * lc;
@@ -838,10 +824,8 @@ static int mean_intensity_internal(vrt_solver* s, SweepStats* stats, double* t_o
                     const size_t shm = 2 * sizeof(double) * OP_TC * (size_t)((int)lc | 1);
                     const int grid = (int)std::min<int64_t>((n + OP_TC - 1) / OP_TC, 148 * 16);
                     if (shm > 48 * 1024) VRT_CUDA(cudaFuncSetAttribute(k_opacity, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
-                    JDirs none;
-                    none.nd = 0;
                     k_opacity<<<grid, OP_THREADS, shm>>>(n, lc, s->lam_dev.p + s->l_begin + l0, s->ld, od, s->gamma.p, s->dD.p, s->vz.p,
-                                                        s->vx.p, s->vy.p, s->pops.p, s->alpha_cont.p, none, nullptr, 0, 0);
+                                                        s->vx.p, s->vy.p, s->pops.p, s->alpha_cont.p);
                     VRT_CUDA(cudaEventRecord(e1));
                     VRT_CUDA(cudaGetLastError());
                     stats->kernels += 1;
@@ -873,12 +857,8 @@ static int mean_intensity_internal(vrt_solver* s, SweepStats* stats, double* t_o
         if (t_sweep_ms) *t_sweep_ms = stats->sweep_ms;
         return VRT_OK;
     }
-    const bool fuse_J = s->is_line && !getenv("VRT_NO_FUSED_J");
     for (int64_t l0 = 0; l0 < s->nlam; l0 += s->lc) {
         int64_t lc = std::min(s->lc, s->nlam - l0);
-        JDirs pend;          // the previous batch's J += Σ w I, folded into this batch's opacity kernel
-        pend.nd = 0;
-        int pend_first = 0;
         for (int d0 = 0; d0 < s->nd; d0 += s->db) {
             int nb = std::min(s->db, s->nd - d0);
             std::vector<SweepDir> dirs(nb);
@@ -895,27 +875,6 @@ static int mean_intensity_internal(vrt_solver* s, SweepStats* stats, double* t_o
                 od.alpha[j] = s->alpha_p[j];
                 jd.I[j] = s->I_p[j];
                 jd.w[j] = s->qw[d];
-            }
-            if (s->is_line) {
-                cudaEvent_t o0, o1;
-                VRT_TRY(s->event(&o0));
-                VRT_TRY(s->event(&o1));
-                op_ev.emplace_back(o0, o1);
-                VRT_CUDA(cudaEventRecord(o0));
-                {
-                    const size_t shm = 2 * sizeof(double) * OP_TC * (size_t)((int)lc | 1);
-                    const int grid = (int)std::min<int64_t>((n + OP_TC - 1) / OP_TC, 148 * 16);
-                    if (shm > 48 * 1024) VRT_CUDA(cudaFuncSetAttribute(k_opacity, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
-                    // reads the previous batch's intensities (pend) BEFORE the boundary kernels below overwrite those buffers
-                    k_opacity<<<grid, OP_THREADS, shm>>>(n, lc, s->lam_dev.p + s->l_begin + l0, s->ld, od, s->gamma.p, s->dD.p, s->vz.p,
-                                                        s->vx.p, s->vy.p, s->pops.p, s->alpha_cont.p, pend, s->J.p + l0, s->nlam, pend_first);
-                    pend.nd = 0;
-                }
-                VRT_CUDA(cudaEventRecord(op_ev.back().second));
-                stats->kernels += 1;
-            }
-            for (int j = 0; j < nb; j++) {
-                int d = s->order[d0 + j];
                 // boundary values (lambda_iteration.jl:98-106 / lambda_continuum.jl:44-51) + the never-processed site (Q1)
                 if (!s->qdown[d]) {
                     k_boundary_planck<<<nblocks(s->n1_up * lc, 256), 256>>>(s->I_p[j], lc, s->lam_dev.p + s->l_begin + l0, s->T.p,
@@ -928,16 +887,27 @@ static int mean_intensity_internal(vrt_solver* s, SweepStats* stats, double* t_o
                 }
                 stats->kernels += 1;
             }
+            if (s->is_line) {
+                cudaEvent_t o0, o1;
+                VRT_TRY(s->event(&o0));
+                VRT_TRY(s->event(&o1));
+                op_ev.emplace_back(o0, o1);
+                VRT_CUDA(cudaEventRecord(o0));
+                {
+                    const size_t shm = 2 * sizeof(double) * OP_TC * (size_t)((int)lc | 1);
+                    const int grid = (int)std::min<int64_t>((n + OP_TC - 1) / OP_TC, 148 * 16);
+                    if (shm > 48 * 1024) VRT_CUDA(cudaFuncSetAttribute(k_opacity, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
+                    k_opacity<<<grid, OP_THREADS, shm>>>(n, lc, s->lam_dev.p + s->l_begin + l0, s->ld, od, s->gamma.p, s->dD.p, s->vz.p,
+                                                        s->vx.p, s->vy.p, s->pops.p, s->alpha_cont.p);
+                }
+                VRT_CUDA(cudaEventRecord(op_ev.back().second));
+                stats->kernels += 1;
+            }
             VRT_CUDA(cudaGetLastError());
             VRT_TRY(wait_gather(s));   // the sweep reads S of every cell
             VRT_TRY(sweep_run(s->g, nb, dirs.data(), s->S.p + l0, s->nlam, lc, 0, stats));
-            if (fuse_J && d0 + s->db < s->nd) {   // not the last batch of this wavelength chunk: the next opacity kernel adds it
-                pend = jd;
-                pend_first = d0 == 0;
-            } else {
-                k_J_reduce<<<nblocks(n * lc, 256), 256>>>(n, lc, jd, s->J.p + l0, s->nlam, d0 == 0);
-                stats->kernels += 1;
-            }
+            k_J_reduce<<<nblocks(n * lc, 256), 256>>>(n, lc, jd, s->J.p + l0, s->nlam, d0 == 0);
+            stats->kernels += 1;
             VRT_CUDA(cudaGetLastError());
         }
     }
