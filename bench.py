@@ -384,35 +384,49 @@ def main():
     sites = V.VoronoiSites(*cell, atm["temperature"], atm["electron_density"], atm["hydrogen_density"], atm["velocity_z"],
                            atm["velocity_x"], atm["velocity_y"], b["z_min"], b["z_max"], b["x_min"], b["x_max"], b["y_min"], b["y_max"], n)
     ndirs = int(np.sum(th != 90))
-    def make_solver(mine):
-        my_quad = (w[mine], th[mine], ph[mine]) if D > 1 else P["qpath"]
-        return V.Solver(sites, my_quad, line=line, α_cont=α_cont, ελ=ελ, C_rates=Cr, LTE_pops=lte,
-                        lam_range=(lo, hi) if G > 1 else None, dir_range=(0, len(mine)) if D > 1 else None,
-                        cell_shard=(di, D) if D > 1 and not os.environ.get("VRT_NO_CELL_SHARD") else None)
+    def make_solver(mine, pieces=()):
+        """solver of this rank: the whole directions `mine` plus the wavelength parts `pieces` = [(direction, lo, hi)]"""
+        rows = sorted(set(int(i) for i in mine) | set(int(p[0]) for p in pieces))
+        my_quad = (w[rows], th[rows], ph[rows]) if D > 1 else P["qpath"]
+        sol = V.Solver(sites, my_quad, line=line, α_cont=α_cont, ελ=ελ, C_rates=Cr, LTE_pops=lte,
+                       lam_range=(lo, hi) if G > 1 else None, dir_range=(0, len(rows)) if D > 1 else None,
+                       cell_shard=(di, D) if D > 1 and not os.environ.get("VRT_NO_CELL_SHARD") else None)
+        for (i, plo, phi) in pieces:
+            sol.set_direction_lambda(rows.index(int(i)), plo, phi)
+        return sol
     mine = round_robin(int(nq), D, di)
+    pieces = []
     solver = make_solver(mine)
     balance = None
     if D > 1 and not os.environ.get("VRT_ROUND_ROBIN"):
         # balance the direction shards by the measured work of each direction (visits of its sweep program): every rank
-        # reports the directions it built, the table is all-gathered, and the shards are re-dealt longest-first
+        # reports the directions it built, the table is all-reduced, and the shards are re-dealt: whole directions longest
+        # first, and — when the direction count does not divide by the shard count — the most expensive ones split by wavelength
         cost = torch.zeros(int(nq), dtype=torch.float64, device="cuda")
         cost[torch.as_tensor(mine, device="cuda")] = torch.as_tensor(solver.direction_visits(), device="cuda")
         dist.all_reduce(cost, op=dist.ReduceOp.MAX)
         costs = cost.cpu().numpy()
-        shards, load = lpt_assign(list(costs), D)
         rr_load = [float(costs[round_robin(int(nq), D, r)].sum()) for r in range(D)]
-        balance = {"how": "longest processing time first on the visits of each direction's sweep program",
-                   "max_over_mean_load": max(load) / (sum(load) / D), "round_robin_max_over_mean_load": max(rr_load) / (sum(rr_load) / D)}
-        if not np.array_equal(shards[di], mine):
+        sp = None if (G > 1 or os.environ.get("VRT_NO_SPLIT")) else split_assign(list(costs), D, nlam)
+        if sp is not None:
+            plan, load = sp
+            new_mine, new_pieces = plan[di]
+            how = f"{len(new_mine)} whole directions per shard (longest processing time first) + the {int(nq) % D} most expensive directions split by wavelength into {D // (int(nq) % D)} parts (vrt_solver_set_direction_lambda)"
+        else:
+            shards, load = lpt_assign(list(costs), D)
+            new_mine, new_pieces = shards[di], []
+            how = "longest processing time first on the visits of each direction's sweep program"
+        balance = {"how": how, "max_over_mean_load": max(load) / (sum(load) / D), "round_robin_max_over_mean_load": max(rr_load) / (sum(rr_load) / D)}
+        if not np.array_equal(new_mine, mine) or new_pieces:
             solver.close()
             _lib.check(_lib.lib().vrt_grid_release_schedules(sites._grid.h))
-            mine = shards[di]
-            solver = make_solver(mine)
+            mine, pieces = new_mine, new_pieces
+            solver = make_solver(mine, pieces)
     coll = {"ms": 0.0, "bytes": 0}
     comm_how = None
     if world > 1:
         comm_how = attach_collectives(solver, dist, torch, local_rank, rank, world, D, G, di, gi, coll)
-    log(f"setup {time.time() - t_setup:.1f}s: n={n} dirs={ndirs} nlam={nlam} shards: {D} direction x {G} wavelength; rank 0 has directions {list(mine)} wavelengths [{lo},{hi}) layers up/down={len(sites.layers_up) - 1}/{len(sites.layers_down) - 1}")
+    log(f"setup {time.time() - t_setup:.1f}s: n={n} dirs={ndirs} nlam={nlam} shards: {D} direction x {G} wavelength; rank 0 has directions {[int(i) for i in mine]} + parts {[(int(a), int(b), int(c)) for a, b, c in pieces]} wavelengths [{lo},{hi}) layers up/down={len(sites.layers_up) - 1}/{len(sites.layers_down) - 1}")
 
     def sync():
         torch.cuda.synchronize()
@@ -447,7 +461,7 @@ def main():
 
     # ---- roofline of the dominant kernel (k_sweep): algorithmic bytes / measured kernel time (CUDA events in the library)
     B_alg = 40.0 + 104.0 / nlam
-    local_updates = float(n) * int(np.sum(th[mine] != 90)) * (hi - lo)
+    local_updates = float(n) * (int(np.sum(th[mine] != 90)) * (hi - lo) + sum(p[2] - p[1] for p in pieces))
     launches = max(stats["kernels"], 1)
     achieved = B_alg * local_updates * K / (stats["sweep_ms"] / 1e3) / 1e9 if stats["sweep_ms"] > 0 else 0.0
     peak, peak_src = measured_peak()
@@ -587,6 +601,41 @@ def lpt_assign(costs, D):
         out[r].append(i)
         load[r] += costs[i]
     return [np.array(sorted(v), dtype=np.int64) for v in out], load
+
+
+def split_assign(costs, D, nlam, min_width=16):
+    """Directions that do not divide evenly over D shards: the nq % D most expensive ones are split by wavelength into D / (nq % D)
+    parts each (vrt_solver_set_direction_lambda), so that every shard gets nq // D whole directions plus one part — 20 directions on
+    8 shards: two whole ones and one half each.  -> per shard (whole direction indices, [(direction, lam_lo, lam_hi)]), loads;
+    None when the counts do not allow it (then lpt_assign)."""
+    nq = len(costs)
+    q, r = divmod(nq, D)
+    if r == 0 or D % r != 0:
+        return None
+    parts = D // r
+    if nlam // parts < min_width:
+        return None
+    order = sorted(range(nq), key=lambda i: (-costs[i], i))
+    split, whole = order[:r], order[r:]
+    shards, load = lpt_assign([costs[i] for i in whole], D)
+    shards = [np.array(sorted(whole[j] for j in sh), dtype=np.int64) for sh in shards]
+    # a pass over a fraction f of the wavelengths costs about 0.3 + 0.7 f of a full one (measured: half rows 0.65)
+    frac = 1.0 / parts
+    pieces = []
+    for i in split:
+        for k in range(parts):
+            lo = (nlam * k) // parts
+            hi = (nlam * (k + 1)) // parts
+            pieces.append((costs[i] * (0.3 + 0.7 * frac), i, lo, hi))
+    pieces.sort(key=lambda t: (-t[0], t[1], t[2]))
+    extra = [[] for _ in range(D)]
+    free = set(range(D))
+    for c, i, lo, hi in pieces:
+        rnk = min(free, key=lambda j: (load[j], j))
+        free.discard(rnk)
+        extra[rnk].append((i, lo, hi))
+        load[rnk] += c
+    return [(shards[j], extra[j]) for j in range(D)], load
 
 
 def round_robin(nq, D, di):

@@ -308,6 +308,13 @@ int vrt_solver_comm_init(vrt_solver* s, const char* dir_id, int32_t dir_rank, in
  * over processes balances them with it (longest processing time first) instead of dealing them round-robin. */
 int vrt_solver_direction_visits(const vrt_solver* s, int64_t* n_dirs, double* visits, int64_t capacity);
 
+/* Restricts one direction of this solver (index into its quadrature table without the θ = 90 rows) to the local wavelengths
+ * [lam_begin, lam_end): the direction is then shared with another process that takes the remaining wavelengths (both add
+ * their part into J before the reduction over the direction group).  This is how 20 directions balance on 8 processes: two
+ * whole directions each plus one half of a ninth.  lam_begin == lam_end == 0 or the full range restores the default.  Line
+ * solver on a Voronoi grid only; a sub-range needs at least 16 wavelengths (it runs the wide-row sweep program). */
+int vrt_solver_set_direction_lambda(vrt_solver* s, int32_t direction, int64_t lam_begin, int64_t lam_end);
+
 /* (Re)upload one per-site input of the line solver.  In the reference these are plain function arguments
  * (α_cont of J_λ_voronoi, LTE_pops of calculate_R, C of get_revised_populations), so a drop-in caller may
  * hand them over late or change them between calls.  Shapes as in vrt_site_data. */

@@ -262,6 +262,10 @@ function comm_init!(solver::Ptr{Cvoid}; dir_id=nothing, dir_rank=0, dir_size=1, 
     check(ccall((:vrt_solver_comm_init, libvrt), Cint, (Ptr{Cvoid}, Ptr{UInt8}, Int32, Int32, Ptr{UInt8}, Int32, Int32), solver,
                 dir_id === nothing ? C_NULL : pointer(dir_id), dir_rank, dir_size, lam_id === nothing ? C_NULL : pointer(lam_id), lam_rank, lam_size))
 end
+# direction `d` (0-based index in the solver's own table) on the local wavelengths [lo, hi) only: a direction shared with another
+# process that takes the rest (20 directions on 8 GPUs: two whole directions and half of a ninth each)
+set_direction_lambda!(solver::Ptr{Cvoid}, d::Integer, lo::Integer, hi::Integer) =
+    check(ccall((:vrt_solver_set_direction_lambda, libvrt), Cint, (Ptr{Cvoid}, Int32, Int64, Int64), solver, d, lo, hi))
 # this process's cells [first, last) in internal order (internal cell c is site perm_up[c+1]) and its slice of the state
 function cell_slice(solver::Ptr{Cvoid})
     a = Ref{Int64}(0); b = Ref{Int64}(0)

@@ -417,3 +417,31 @@ def test_direction_shards_sum_to_full_J(V, oracle):
         Jsum += sh.mean_intensity(S, P["lte"])
         sh.close()
     assert rel_err(Jsum, Jf) < 1e-13
+
+
+def test_direction_split_by_wavelength_adds_up(V, oracle):
+    """vrt_solver_set_direction_lambda: a direction shared between two solvers, each taking part of its wavelengths (how 20
+    directions balance on 8 processes), gives the same J as the undivided solve"""
+    from voronoirt_b200 import atom
+    P = line_problem(V, oracle, "grid_strat3000", nbb=50, nbf=20)
+    line, sites = P["line"], P["sites"]
+    nlam = len(line.λ)
+    w, th, ph, nq = quad(V, "ul7n12")
+    pick = [1, 2, 9]
+    S = np.asfortranarray(atom.B_λ(line.λ[:, None], sites.temperature[None, :]))
+    ref = V.Solver(sites, (w[pick], th[pick], ph[pick]), line=line, α_cont=P["α_cont"], LTE_pops=P["lte"])
+    Jref = ref.mean_intensity(S, P["lte"])
+    ref.close()
+    half = nlam // 2
+    a = V.Solver(sites, (w[pick], th[pick], ph[pick]), line=line, α_cont=P["α_cont"], LTE_pops=P["lte"])
+    a.set_direction_lambda(2, 0, half)                       # two whole directions + the lower half of the third
+    Ja = a.mean_intensity(S, P["lte"])
+    a.close()
+    b = V.Solver(sites, (w[pick[2:]], th[pick[2:]], ph[pick[2:]]), line=line, α_cont=P["α_cont"], LTE_pops=P["lte"])
+    b.set_direction_lambda(0, half, nlam)                    # only the upper half of the third direction
+    Jb = b.mean_intensity(S, P["lte"])
+    with pytest.raises(Exception):
+        b.set_direction_lambda(0, 0, 5)                      # narrower than the wide-row program allows
+    b.close()
+    assert not Jb[:half].any()                               # nothing outside the assigned wavelengths
+    assert rel_err(Ja + Jb, Jref) < 1e-13

@@ -37,6 +37,26 @@ def test_lpt_balances_better_than_round_robin():
         assert max(load) <= sum(costs) / D + max(costs)                         # the LPT guarantee
 
 
+def test_split_assign_covers_every_direction_and_wavelength_once():
+    import bench
+    rng = np.random.default_rng(4)
+    costs = list(rng.uniform(0.8, 1.5, 20))
+    assert bench.split_assign(costs, 4, 91) is None and bench.split_assign(costs, 2, 91) is None      # 20 divides evenly
+    assert bench.split_assign(costs, 3, 91) is None                                                   # 2 leftovers on 3 shards
+    plan, load = bench.split_assign(costs, 8, 91)
+    cover = np.zeros((20, 91), dtype=int)
+    for whole, pieces in plan:
+        assert len(whole) == 2 and len(pieces) == 1
+        for i in whole:
+            cover[i] += 1
+        for i, lo, hi in pieces:
+            assert hi - lo >= 16
+            cover[i, lo:hi] += 1
+    assert (cover == 1).all()
+    _, lpt = bench.lpt_assign(costs, 8)
+    assert max(load) / np.mean(load) < max(lpt) / np.mean(lpt)
+
+
 WORKER = textwrap.dedent('''
     import os, sys
     import numpy as np

@@ -581,6 +581,10 @@ class Solver:
         """in-library NCCL collectives (include/vrt.h vrt_solver_comm_init); ids are the 128 bytes of nccl_unique_id()"""
         check(lib().vrt_solver_comm_init(self.h, dir_id, int(dir_rank), int(dir_size), lam_id, int(lam_rank), int(lam_size)))
 
+    def set_direction_lambda(self, direction, lam_begin, lam_end):
+        """solve direction `direction` (index in this solver's table) on the local wavelengths [lam_begin, lam_end) only"""
+        check(lib().vrt_solver_set_direction_lambda(self.h, int(direction), int(lam_begin), int(lam_end)))
+
     def direction_visits(self):
         """(cell, sweep) visits of each direction this solver holds (θ = 90 rows left out): the cost used to balance direction shards"""
         nd = C.c_int64()

@@ -478,6 +478,9 @@ struct vrt_solver {
     std::vector<std::array<double, 3>> qk;
     std::vector<DirSchedule*> sch;
     std::vector<int> order;                 // order the directions are swept in (batches of `db` consecutive entries)
+    // wavelength sub-range [lo, hi) of the local wavelengths a direction is solved on (vrt_solver_set_direction_lambda): a
+    // direction shared between two processes, each taking part of its wavelengths.  lo == hi == 0: all local wavelengths.
+    std::vector<std::array<int64_t, 2>> dir_lam;
     int64_t n1_up = 0, n1_dn = 0;
     // per-site device arrays, internal order
     DevBuf<double> T, ne, NH, vz, vx, vy, dD, alpha_cont, eps, B0, Cp, lte, lam_dev, gamma;
@@ -599,6 +602,7 @@ static int solver_common_init(vrt_solver* s, vrt_grid* g, const vrt_quadrature* 
     // directions in this order instead of the order of the quadrature file (rounding-level difference; VRT_DIR_ORDER=0
     // keeps the file order).
     s->order.resize(s->nd);
+    s->dir_lam.assign(s->nd, std::array<int64_t, 2>{0, 0});
     for (int d = 0; d < s->nd; d++) s->order[d] = d;
     {
         const char* e = getenv("VRT_DIR_ORDER");
@@ -703,11 +707,12 @@ static int plan_buffers(vrt_solver* s) {
     s->alpha_p.assign(db, nullptr);
     s->I_p.assign(db, nullptr);
     s->scr_p.assign(db, std::array<double*, MAX_SWEEPS>{});
-    // buffer slot j serves directions j, j+db, ...: size for the largest of them
+    // any direction may end up in any buffer slot (whole and wavelength-split directions are batched separately): every slot is
+    // sized for the largest scratch need
+    int64_t scr[MAX_SWEEPS] = {0};
+    for (int d = 0; d < s->nd; d++)
+        for (int k = 0; k < MAX_SWEEPS; k++) scr[k] = std::max(scr[k], s->sch[d]->scr_rows[k]);
     for (int j = 0; j < db; j++) {
-        int64_t scr[MAX_SWEEPS] = {0};
-        for (int q = j; q < s->nd; q += db)
-            for (int k = 0; k < MAX_SWEEPS; k++) scr[k] = std::max(scr[k], s->sch[s->order[q]]->scr_rows[k]);
         auto* bi = new DevBuf<double>();
         s->bufs.push_back(bi);
         VRT_TRY(bi->alloc((size_t)n * lc + 2));
@@ -857,58 +862,80 @@ static int mean_intensity_internal(vrt_solver* s, SweepStats* stats, double* t_o
         if (t_sweep_ms) *t_sweep_ms = stats->sweep_ms;
         return VRT_OK;
     }
-    for (int64_t l0 = 0; l0 < s->nlam; l0 += s->lc) {
-        int64_t lc = std::min(s->lc, s->nlam - l0);
-        for (int d0 = 0; d0 < s->nd; d0 += s->db) {
-            int nb = std::min(s->db, s->nd - d0);
-            std::vector<SweepDir> dirs(nb);
-            OpacityDirs od;
-            JDirs jd;
-            od.nd = jd.nd = nb;
-            for (int j = 0; j < nb; j++) {
-                int d = s->order[d0 + j];
-                dirs[j].sch = s->sch[d];
-                dirs[j].I_main = s->I_p[j];
-                dirs[j].alpha = s->is_line ? s->alpha_p[j] : s->alpha_cont.p;
-                for (int k = 0; k < MAX_SWEEPS; k++) dirs[j].scratch[k] = s->scr_p[j][k];
-                for (int a = 0; a < 3; a++) od.k[j][a] = s->qk[d][a];
-                od.alpha[j] = s->alpha_p[j];
-                jd.I[j] = s->I_p[j];
-                jd.w[j] = s->qw[d];
-                // boundary values (lambda_iteration.jl:98-106 / lambda_continuum.jl:44-51) + the never-processed site (Q1)
-                if (!s->qdown[d]) {
-                    k_boundary_planck<<<nblocks(s->n1_up * lc, 256), 256>>>(s->I_p[j], lc, s->lam_dev.p + s->l_begin + l0, s->T.p,
-                                                                           s->is_line ? nullptr : s->B0.p, s->n1_up);
-                    VRT_CUDA(cudaMemsetAsync(s->I_p[j] + (size_t)(n - 1) * lc, 0, sizeof(double) * lc));
-                } else {
-                    k_boundary_rows<<<nblocks(s->n1_dn * lc, 256), 256>>>(s->I_p[j], lc, nullptr, s->g->perm_dn_int.p, s->n1_dn);
-                    k_boundary_rows<<<nblocks(lc, 256), 256>>>(s->I_p[j], lc, nullptr, s->g->perm_dn_int.p + (n - 1), 1);
-                    stats->kernels += 1;
-                }
+    // directions solved on all local wavelengths, in sweep order, and those restricted to a wavelength sub-range
+    std::vector<int> full, part;
+    for (int q = 0; q < s->nd; q++) {
+        const int d = s->order[q];
+        (s->dir_lam[d][1] > s->dir_lam[d][0] ? part : full).push_back(d);
+    }
+    bool J_started = false;
+    // one launch group: directions `ds` (at most db) on the local wavelengths [l0, l0 + lc), buffer slots 0 .. ds.size()-1
+    auto run_batch = [&](const std::vector<int>& ds, int64_t l0, int64_t lc, bool first) -> int {
+        const int nb = (int)ds.size();
+        std::vector<SweepDir> dirs(nb);
+        OpacityDirs od;
+        JDirs jd;
+        od.nd = jd.nd = nb;
+        for (int j = 0; j < nb; j++) {
+            const int d = ds[j];
+            dirs[j].sch = s->sch[d];
+            dirs[j].I_main = s->I_p[j];
+            dirs[j].alpha = s->is_line ? s->alpha_p[j] : s->alpha_cont.p;
+            for (int k = 0; k < MAX_SWEEPS; k++) dirs[j].scratch[k] = s->scr_p[j][k];
+            for (int a = 0; a < 3; a++) od.k[j][a] = s->qk[d][a];
+            od.alpha[j] = s->alpha_p[j];
+            jd.I[j] = s->I_p[j];
+            jd.w[j] = s->qw[d];
+            // boundary values (lambda_iteration.jl:98-106 / lambda_continuum.jl:44-51) + the never-processed site (Q1)
+            if (!s->qdown[d]) {
+                k_boundary_planck<<<nblocks(s->n1_up * lc, 256), 256>>>(s->I_p[j], lc, s->lam_dev.p + s->l_begin + l0, s->T.p,
+                                                                       s->is_line ? nullptr : s->B0.p, s->n1_up);
+                VRT_CUDA(cudaMemsetAsync(s->I_p[j] + (size_t)(n - 1) * lc, 0, sizeof(double) * lc));
+            } else {
+                k_boundary_rows<<<nblocks(s->n1_dn * lc, 256), 256>>>(s->I_p[j], lc, nullptr, s->g->perm_dn_int.p, s->n1_dn);
+                k_boundary_rows<<<nblocks(lc, 256), 256>>>(s->I_p[j], lc, nullptr, s->g->perm_dn_int.p + (n - 1), 1);
                 stats->kernels += 1;
             }
-            if (s->is_line) {
-                cudaEvent_t o0, o1;
-                VRT_TRY(s->event(&o0));
-                VRT_TRY(s->event(&o1));
-                op_ev.emplace_back(o0, o1);
-                VRT_CUDA(cudaEventRecord(o0));
-                {
-                    const size_t shm = 2 * sizeof(double) * OP_TC * (size_t)((int)lc | 1);
-                    const int grid = (int)std::min<int64_t>((n + OP_TC - 1) / OP_TC, 148 * 16);
-                    if (shm > 48 * 1024) VRT_CUDA(cudaFuncSetAttribute(k_opacity, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
-                    k_opacity<<<grid, OP_THREADS, shm>>>(n, lc, s->lam_dev.p + s->l_begin + l0, s->ld, od, s->gamma.p, s->dD.p, s->vz.p,
-                                                        s->vx.p, s->vy.p, s->pops.p, s->alpha_cont.p);
-                }
-                VRT_CUDA(cudaEventRecord(op_ev.back().second));
-                stats->kernels += 1;
-            }
-            VRT_CUDA(cudaGetLastError());
-            VRT_TRY(wait_gather(s));   // the sweep reads S of every cell
-            VRT_TRY(sweep_run(s->g, nb, dirs.data(), s->S.p + l0, s->nlam, lc, 0, stats));
-            k_J_reduce<<<nblocks(n * lc, 256), 256>>>(n, lc, jd, s->J.p + l0, s->nlam, d0 == 0);
             stats->kernels += 1;
-            VRT_CUDA(cudaGetLastError());
+        }
+        if (s->is_line) {
+            cudaEvent_t o0, o1;
+            VRT_TRY(s->event(&o0));
+            VRT_TRY(s->event(&o1));
+            op_ev.emplace_back(o0, o1);
+            VRT_CUDA(cudaEventRecord(o0));
+            {
+                const size_t shm = 2 * sizeof(double) * OP_TC * (size_t)((int)lc | 1);
+                const int grid = (int)std::min<int64_t>((n + OP_TC - 1) / OP_TC, 148 * 16);
+                if (shm > 48 * 1024) VRT_CUDA(cudaFuncSetAttribute(k_opacity, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
+                k_opacity<<<grid, OP_THREADS, shm>>>(n, lc, s->lam_dev.p + s->l_begin + l0, s->ld, od, s->gamma.p, s->dD.p, s->vz.p,
+                                                    s->vx.p, s->vy.p, s->pops.p, s->alpha_cont.p);
+            }
+            VRT_CUDA(cudaEventRecord(op_ev.back().second));
+            stats->kernels += 1;
+        }
+        VRT_CUDA(cudaGetLastError());
+        VRT_TRY(wait_gather(s));   // the sweep reads S of every cell
+        VRT_TRY(sweep_run(s->g, nb, dirs.data(), s->S.p + l0, s->nlam, lc, 0, stats));
+        k_J_reduce<<<nblocks(n * lc, 256), 256>>>(n, lc, jd, s->J.p + l0, s->nlam, first ? 1 : 0);
+        stats->kernels += 1;
+        VRT_CUDA(cudaGetLastError());
+        return VRT_OK;
+    };
+    for (int64_t l0 = 0; l0 < s->nlam; l0 += s->lc) {
+        const int64_t lc = std::min(s->lc, s->nlam - l0);
+        for (size_t d0 = 0; d0 < full.size(); d0 += (size_t)s->db) {
+            std::vector<int> ds(full.begin() + d0, full.begin() + std::min(full.size(), d0 + (size_t)s->db));
+            VRT_TRY(run_batch(ds, l0, lc, d0 == 0));
+        }
+    }
+    J_started = !full.empty();
+    if (!part.empty()) {
+        // J of the wavelengths no full direction has written yet starts from zero
+        if (!J_started) VRT_CUDA(cudaMemsetAsync(s->J.p, 0, sizeof(double) * (size_t)n * s->nlam));
+        for (int d : part) {
+            const int64_t lo = s->dir_lam[d][0], hi = s->dir_lam[d][1];
+            for (int64_t l0 = lo; l0 < hi; l0 += s->lc) VRT_TRY(run_batch(std::vector<int>{d}, l0, std::min(s->lc, hi - l0), false));
         }
     }
     VRT_CUDA(cudaDeviceSynchronize());
@@ -1570,6 +1597,27 @@ int vrt_solver_direction_visits(const vrt_solver* s, int64_t* n_dirs, double* vi
         }
         for (int d = 0; d < s->nd; d++) visits[d] = s->sch[d] ? (double)s->sch[d]->n_visits : (double)s->n;
     }
+    return VRT_OK;
+}
+
+int vrt_solver_set_direction_lambda(vrt_solver* s, int32_t direction, int64_t lam_begin, int64_t lam_end) {
+    if (!s) return VRT_E_INVALID;
+    if (s->g->regular || !s->is_line) {
+        set_error("vrt_solver_set_direction_lambda: only for the line solver on a Voronoi grid");
+        return VRT_E_STATE;
+    }
+    if (direction < 0 || direction >= s->nd || lam_begin < 0 || lam_end > s->nlam || lam_end < lam_begin) {
+        set_error("vrt_solver_set_direction_lambda: direction %d or range [%lld, %lld) out of bounds", (int)direction, (long long)lam_begin,
+                  (long long)lam_end);
+        return VRT_E_INVALID;
+    }
+    if (lam_end - lam_begin == s->nlam) lam_begin = lam_end = 0;   // the whole range: nothing special
+    else if (lam_end > lam_begin && chunk_visits(lam_end - lam_begin) != s->sch[direction]->cv) {
+        set_error("vrt_solver_set_direction_lambda: %lld wavelengths need another sweep program than the solver's (use >= 16)",
+                  (long long)(lam_end - lam_begin));
+        return VRT_E_INVALID;
+    }
+    s->dir_lam[direction] = {lam_begin, lam_end};
     return VRT_OK;
 }
 
