@@ -661,19 +661,31 @@ def attach_collectives(solver, dist, torch, local_rank, rank, world, D, G, di, g
                 buf = torch.frombuffer(bytearray(api.nccl_unique_id()), dtype=torch.uint8).cuda()
             if rank in members:
                 dist.broadcast(buf, src=members[0], group=grp)
-                return buf.cpu().numpy().tobytes()
-            return None
-        dir_id = lam_id = None
+                return buf.cpu().numpy().tobytes(), grp
+            return None, None
+        dir_id = lam_id = my_dir_group = None
         for g in range(G):
             if D > 1:
-                r = group_id([g * D + d for d in range(D)])
-                dir_id = r if g == gi else dir_id
+                r, grp = group_id([g * D + d for d in range(D)])
+                if g == gi:
+                    dir_id, my_dir_group = r, grp
         for d in range(D):
             if G > 1:
-                r = group_id([g * D + d for g in range(G)])
+                r, _ = group_id([g * D + d for g in range(G)])
                 lam_id = r if d == di else lam_id
         solver.comm_init(dir_id, di, D, lam_id, gi, G)
-        return ("collectives inside libvrt.so (ncclCommInitRank from a broadcast unique id, own stream): reduce-scatter of J, all-gather of S and the "
+        how_J = "reduce-scatter of J"
+        if D > 1 and not os.environ.get("VRT_NO_PEER_REDUCE") and not os.environ.get("VRT_NO_CELL_SHARD"):
+            # J reduced through peer memory: the CUDA IPC handles of the J buffers travel once (64 bytes per rank)
+            mine_h = torch.frombuffer(bytearray(solver.peer_handle()), dtype=torch.uint8).cuda()
+            allh = torch.zeros(64 * D, dtype=torch.uint8, device="cuda")
+            dist.all_gather_into_tensor(allh, mine_h, group=my_dir_group)
+            try:
+                solver.peer_attach(allh.cpu().numpy().tobytes())
+                how_J = "J reduced through peer memory (CUDA IPC over NVLink) inside the source-update kernel"
+            except Exception as ex:  # noqa: BLE001
+                log(f"peer-memory reduction not available ({ex}); using the NCCL reduce-scatter")
+        return (f"collectives inside libvrt.so (ncclCommInitRank from a broadcast unique id, own stream): {how_J}, all-gather of S and the "
                 "populations, all-reduce of the rates over wavelength shards, max of the criterion; source update, rates and statistical equilibrium sharded over cells")
 
     class _Dev:

@@ -308,6 +308,16 @@ int vrt_solver_comm_init(vrt_solver* s, const char* dir_id, int32_t dir_rank, in
  * over processes balances them with it (longest processing time first) instead of dealing them round-robin. */
 int vrt_solver_direction_visits(const vrt_solver* s, int64_t* n_dirs, double* visits, int64_t capacity);
 
+/* Reduction of J through peer memory instead of a reduce-scatter (one node, NVLink / NVSwitch).  Every process of the direction
+ * group exports its J buffer (vrt_solver_peer_handle: a 64-byte CUDA IPC handle), the host gathers the handles of the group in
+ * rank order (dir_size x 64 bytes) and hands them to every member (vrt_solver_peer_attach).  From then on vrt_lambda_iterate
+ * replaces "reduce-scatter J, then update S on the own cell slice" by ONE kernel that reads the slice from all peers' buffers
+ * over NVLink, adds them in rank order, keeps the sum as its J and updates S.  Needs vrt_solver_comm_init (the barrier in front
+ * of the kernel is a one-element all-reduce) and cell shards.  If the handles cannot be opened the call fails and the solver keeps
+ * using the reduce-scatter. */
+int vrt_solver_peer_handle(vrt_solver* s, char handle[64]);
+int vrt_solver_peer_attach(vrt_solver* s, const char* handles, int32_t count);
+
 /* Restricts one direction of this solver (index into its quadrature table without the θ = 90 rows) to the local wavelengths
  * [lam_begin, lam_end): the direction is then shared with another process that takes the remaining wavelengths (both add
  * their part into J before the reduction over the direction group).  This is how 20 directions balance on 8 processes: two

@@ -33,6 +33,14 @@ def _ferry_id(dist, torch, api, rank, src=0):
     return buf.cpu().numpy().tobytes()
 
 
+def _attach_peers(dist, torch, s, world):
+    """J reduced through peer memory: every rank's 64-byte IPC handle, gathered in rank order"""
+    mine = torch.frombuffer(bytearray(s.peer_handle()), dtype=torch.uint8).cuda()
+    allh = torch.zeros(64 * world, dtype=torch.uint8, device="cuda")
+    dist.all_gather_into_tensor(allh, mine)
+    s.peer_attach(allh.cpu().numpy().tobytes())
+
+
 def _worker(rank, world, port, q, mode):
     import sys
     sys.path.insert(0, ROOT)
@@ -84,9 +92,11 @@ def _worker(rank, world, port, q, mode):
         return
     dlo, dhi = bench.shard_range(12, world, rank)
     s = V.Solver(sites, qp, line=line, α_cont=α_cont, ελ=ελ, C_rates=Cr, LTE_pops=lte, dir_range=(dlo, dhi), cell_shard=(rank, world))
-    if mode == "nccl":
+    if mode in ("nccl", "peers"):
         assert _lib.lib().vrt_nccl_available() == 1
         s.comm_init(dir_id=_ferry_id(dist, torch, api, rank), dir_rank=rank, dir_size=world)
+        if mode == "peers":
+            _attach_peers(dist, torch, s, world)
     else:
         class _Dev:
             def __init__(self, ptr, count):
@@ -143,7 +153,7 @@ def rel(a, b):
     return np.abs(a - b).max() / np.abs(b).max()
 
 
-@pytest.mark.parametrize("mode", ["hook", "nccl"])
+@pytest.mark.parametrize("mode", ["hook", "nccl", "peers"])
 def test_two_rank_direction_shards_match_single_gpu(mode):
     import torch
     if torch.cuda.device_count() < 2:

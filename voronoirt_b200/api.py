@@ -593,6 +593,16 @@ class Solver:
         check(lib().vrt_solver_direction_visits(self.h, C.byref(nd), out, nd.value))
         return np.array(out[:nd.value])
 
+    def peer_handle(self):
+        """64-byte CUDA IPC handle of this solver's J buffer (vrt_solver_peer_handle)"""
+        raw = C.create_string_buffer(64)
+        check(lib().vrt_solver_peer_handle(self.h, raw))
+        return raw.raw
+
+    def peer_attach(self, handles):
+        """handles of the whole direction group in rank order (bytes, 64 per rank): J is then reduced through peer memory"""
+        check(lib().vrt_solver_peer_attach(self.h, handles, len(handles) // 64))
+
     def cell_slice(self):
         """[first, last) of the cells this process owns, in internal order (site perm_up[c])"""
         a, b = C.c_int64(), C.c_int64()

@@ -252,6 +252,38 @@ __global__ void k_source_update(int64_t n, int64_t nlam, const double* __restric
     block_max_nan(dmax, isn, diff_bits, diff_nan);
 }
 
+// The same, fused with the reduction of J over the direction shards THROUGH PEER MEMORY (NVLink / NVSwitch): every process
+// holds its partial J (the sum over its own directions) in a buffer the others have mapped (CUDA IPC); the owner of a cell
+// slice reads that slice from all R buffers, adds them in rank order, keeps the sum as its J and updates S — one pass, no
+// reduce-scatter in front of it (the collective would move the same bytes first and this kernel would read them again).
+constexpr int MAX_PEERS = 16;
+struct PeerJ {
+    const double* J[MAX_PEERS];
+    int R;
+};
+__global__ void k_source_update_peers(int64_t n, int64_t nlam, const double* __restrict__ lam, const double* __restrict__ T,
+                                      const double* __restrict__ eps, const PeerJ P, int64_t off, double* __restrict__ Jown,
+                                      double* __restrict__ S, unsigned long long* diff_bits, int* diff_nan) {
+    int64_t total = n * nlam;
+    double dmax = 0.0;
+    bool isn = false;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t c = i / nlam, l = i - c * nlam;
+        double J = 0.0;
+        for (int r = 0; r < P.R; r++) J += __ldcg(P.J[r] + off + i);
+        Jown[i] = J;
+        double e = eps[c];
+        double B = B_lambda(lam[l], T[c]);
+        double s_old = S[i];
+        double s_new = (1 - e) * J + e * B;
+        S[i] = s_new;
+        double d = fabs(1 - s_old / s_new);
+        if (d != d) isn = true;
+        else dmax = fmax(dmax, d);
+    }
+    block_max_nan(dmax, isn, diff_bits, diff_nan);
+}
+
 // criterion alone (first pass of the while loop: S_old = 0)
 __global__ void k_criterion(int64_t n, int64_t nlam, const double* __restrict__ S_new, const double* __restrict__ S_old,
                             const double* __restrict__ eps, int use_thick, unsigned long long* diff_bits, int* diff_nan) {
@@ -506,6 +538,8 @@ struct vrt_solver {
     void* allreduce_user = nullptr;
     void* comm = nullptr;                   // in-library NCCL communicators (comm.cu), preferred over the host hook
     cudaEvent_t comm_ev[2] = {nullptr, nullptr};
+    const double* peerJ[16] = {nullptr};    // J buffers of the direction group mapped through CUDA IPC (own entry = own buffer)
+    bool peers = false;
     cudaEvent_t gather_ev = nullptr;        // a deferred all-gather of S is running on the collectives' stream until this event
     bool gather_pending = false;
     bool has_exchange() const { return comm != nullptr || allreduce != nullptr; }
@@ -527,6 +561,9 @@ struct vrt_solver {
         for (auto e : comm_ev)
             if (e) cudaEventDestroy(e);
         if (gather_ev) cudaEventDestroy(gather_ev);
+        if (peers)
+            for (int r = 0; r < 16; r++)
+                if (peerJ[r] && r != cell_r) cudaIpcCloseMemHandle(const_cast<double*>(peerJ[r]));
         if (comm) vrt::comm_free(comm);
     }
 };
@@ -785,7 +822,9 @@ static int wait_gather(vrt_solver* s) {
 
 // J_λ_voronoi on device state: s->S -> s->J (internal order)
 // scatter: false = all-reduce J over the direction shards (every rank gets the full J); true = reduce-scatter over cells
-static int mean_intensity_internal(vrt_solver* s, SweepStats* stats, double* t_opacity_ms, double* t_sweep_ms, bool scatter = false) {
+// jmode: what happens to the partial J of a direction shard: 0 all-reduce (every rank gets the full J), 1 reduce-scatter over
+// cells, 2 nothing (the owners of the cell slices read it through peer memory)
+static int mean_intensity_internal(vrt_solver* s, SweepStats* stats, double* t_opacity_ms, double* t_sweep_ms, int jmode = 0) {
     const int64_t n = s->n;
     VRT_TRY(plan_buffers(s));
     s->ev_used = 0;
@@ -948,8 +987,8 @@ static int mean_intensity_internal(vrt_solver* s, SweepStats* stats, double* t_o
     if (s->nd == 0) VRT_CUDA(cudaMemset(s->J.p, 0, sizeof(double) * (size_t)n * s->nlam));   // no direction: J = 0, whatever J held
     if (s->dir_sharded && s->has_exchange()) {
         // J = sum over the direction shards (lambda_iteration.jl:102,107 add the directions one after the other)
-        if (scatter) VRT_TRY(exchange(s, s->J.p, s->n_pad * s->nlam, 3));
-        else VRT_TRY(exchange(s, s->J.p, n * s->nlam, 2));
+        if (jmode == 1) VRT_TRY(exchange(s, s->J.p, s->n_pad * s->nlam, 3));
+        else if (jmode == 0) VRT_TRY(exchange(s, s->J.p, n * s->nlam, 2));
     }
     if (t_opacity_ms) *t_opacity_ms = opacity_ms;
     if (t_sweep_ms) *t_sweep_ms = stats->sweep_ms;
@@ -1393,13 +1432,26 @@ int vrt_lambda_iterate(vrt_solver* s, double eps, int32_t maxiter, vrt_iter_cb c
         vrt_iter_info info;
         memset(&info, 0, sizeof(info));
         info.diff = diff;
-        VRT_TRY(mean_intensity_internal(s, &stats, &info.t_opacity_ms, &info.t_sweep_ms, cshard));
+        const bool via_peers = cshard && s->peers && s->comm && !getenv("VRT_NO_PEER_REDUCE");
+        VRT_TRY(mean_intensity_internal(s, &stats, &info.t_opacity_ms, &info.t_sweep_ms, cshard ? (via_peers ? 2 : 1) : 0));
+        if (via_peers) {
+            // every process's partial J must be complete before a peer reads it: a one-element all-reduce is the barrier
+            VRT_TRY(s->diff_pair.ensure(2));
+            VRT_TRY(exchange(s, s->diff_pair.p, 1, 1));
+        }
         cudaEvent_t e[4];
         for (auto& ev : e) VRT_TRY(s->event(&ev));   // pooled: mean_intensity_internal reset the pool for this iteration
         VRT_CUDA(cudaMemset(s->diff_bits.p, 0, sizeof(unsigned long long)));
         VRT_CUDA(cudaMemset(s->diff_nan.p, 0, sizeof(int)));
         VRT_CUDA(cudaEventRecord(e[0]));
-        if (cn > 0)
+        if (cn > 0 && via_peers) {
+            PeerJ pj;
+            pj.R = s->cell_R;
+            for (int r = 0; r < s->cell_R; r++) pj.J[r] = s->peerJ[r];
+            k_source_update_peers<<<nblocks(cn * s->nlam, 256), 256>>>(cn, s->nlam, s->lam_dev.p + s->l_begin, s->T.p + c0, s->eps.p + c0, pj,
+                                                                       c0 * s->nlam, s->J.p + c0 * s->nlam, s->S.p + c0 * s->nlam,
+                                                                       s->diff_bits.p, s->diff_nan.p);
+        } else if (cn > 0)
             k_source_update<<<nblocks(cn * s->nlam, 256), 256>>>(cn, s->nlam, s->lam_dev.p + s->l_begin, s->T.p + c0,
                                                                  s->is_line ? nullptr : s->B0.p + c0, s->eps.p + c0, s->J.p + c0 * s->nlam,
                                                                  s->S.p + c0 * s->nlam, use_thick, s->diff_bits.p, s->diff_nan.p);
@@ -1597,6 +1649,43 @@ int vrt_solver_direction_visits(const vrt_solver* s, int64_t* n_dirs, double* vi
         }
         for (int d = 0; d < s->nd; d++) visits[d] = s->sch[d] ? (double)s->sch[d]->n_visits : (double)s->n;
     }
+    return VRT_OK;
+}
+
+int vrt_solver_peer_handle(vrt_solver* s, char handle[64]) {
+    if (!s || !handle) return VRT_E_INVALID;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handles are 64 bytes");
+    cudaIpcMemHandle_t h;
+    VRT_CUDA(cudaIpcGetMemHandle(&h, s->J.p));
+    memcpy(handle, &h, 64);
+    return VRT_OK;
+}
+
+int vrt_solver_peer_attach(vrt_solver* s, const char* handles, int32_t count) {
+    if (!s || !handles) return VRT_E_INVALID;
+    if (count != s->cell_R || count > 16 || s->cell_R < 2) {
+        set_error("vrt_solver_peer_attach: %d handles for %d cell shards (at most 16)", (int)count, s->cell_R);
+        return VRT_E_INVALID;
+    }
+    if (s->peers) return VRT_OK;
+    for (int r = 0; r < count; r++) {
+        if (r == s->cell_r) {
+            s->peerJ[r] = s->J.p;
+            continue;
+        }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, handles + (size_t)64 * r, 64);
+        void* p = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            for (int q = 0; q < r; q++)
+                if (q != s->cell_r && s->peerJ[q]) cudaIpcCloseMemHandle(const_cast<double*>(s->peerJ[q]));
+            for (auto& pp : s->peerJ) pp = nullptr;
+            return cuda_fail(e, "cudaIpcOpenMemHandle (peer J buffer)", __FILE__, __LINE__);
+        }
+        s->peerJ[r] = static_cast<const double*>(p);
+    }
+    s->peers = true;
     return VRT_OK;
 }
 
