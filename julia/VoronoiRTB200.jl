@@ -262,6 +262,15 @@ function comm_init!(solver::Ptr{Cvoid}; dir_id=nothing, dir_rank=0, dir_size=1, 
     check(ccall((:vrt_solver_comm_init, libvrt), Cint, (Ptr{Cvoid}, Ptr{UInt8}, Int32, Int32, Ptr{UInt8}, Int32, Int32), solver,
                 dir_id === nothing ? C_NULL : pointer(dir_id), dir_rank, dir_size, lam_id === nothing ? C_NULL : pointer(lam_id), lam_rank, lam_size))
 end
+# J reduced through peer memory (one node): every process exports the 64-byte CUDA IPC handle of its J buffer, the host gathers
+# them in rank order (MPI.Allgather) and attaches them; vrt_lambda_iterate then fuses the reduction into the source update
+function peer_handle(solver::Ptr{Cvoid})
+    h = Vector{UInt8}(undef, 64)
+    check(ccall((:vrt_solver_peer_handle, libvrt), Cint, (Ptr{Cvoid}, Ptr{UInt8}), solver, h))
+    return h
+end
+peer_attach!(solver::Ptr{Cvoid}, handles::Vector{UInt8}) =
+    check(ccall((:vrt_solver_peer_attach, libvrt), Cint, (Ptr{Cvoid}, Ptr{UInt8}, Int32), solver, handles, length(handles) ÷ 64))
 # direction `d` (0-based index in the solver's own table) on the local wavelengths [lo, hi) only: a direction shared with another
 # process that takes the rest (20 directions on 8 GPUs: two whole directions and half of a ninth each)
 set_direction_lambda!(solver::Ptr{Cvoid}, d::Integer, lo::Integer, hi::Integer) =
