@@ -684,6 +684,7 @@ def _quad_key(quadrature):
 
 
 def _line_solver(sites, line, quadrature, **kw):
+    # id(line) is a safe key: the cached Solver keeps `line` alive (Solver.line), so the id cannot be reused while the entry exists
     key = ("line", id(line), _quad_key(quadrature))
     s = sites._grid.solvers.get(key)
     if s is None:
