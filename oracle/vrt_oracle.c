@@ -12,6 +12,10 @@
  *   - an independent pure-Python restatement (tests/pyref.py) and the values of SURVEY.md App. F.
  * Third-party arithmetic (Transparency.jl, unpinned, un-vendored): voigt_profile is restated from the
  * published Humlíček (1982, JQSRT 27, 437) w4 algorithm that Transparency.jl implements.
+ * Standard-library arithmetic: `norm(p_d)` (voronoi_utils.jl:238) is LinearAlgebra.generic_norm2, which takes its unscaled
+ * branch whenever n·max|x|² is finite and non-zero — sqrt of the left-to-right sum of squares, exactly what orc_calc_delaunay_lines
+ * computes; `inv(A)*b` (populations.jl:214) goes through LAPACK getrf/getri of whatever BLAS Julia ships and is restated as an LU
+ * solve (last-bit differences of the 2 x 2 solve are inside the 1e-6 population tolerance and cannot be pinned from here).
  *
  * Every function cites the reference file:line it follows (paths relative to the reference root).
  * All arrays use the Julia (column-major, 1-based ids) layouts.  Float64 throughout; compile with
