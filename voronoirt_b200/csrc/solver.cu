@@ -165,11 +165,8 @@ __global__ void __launch_bounds__(OP_THREADS) k_opacity(int64_t n, int64_t lc, c
             }
             __syncthreads();
             double* __restrict__ out = D.alpha[d] + c0 * lc;
-            const int total = ncell * (int)lc;
-            for (int i = threadIdx.x; i < total; i += OP_THREADS) {
-                const int r = i / (int)lc, l = i - r * (int)lc;
-                out[i] = tile[r * ldt + l];
-            }
+            for (int r = warp; r < ncell; r += nwarp)                      // a warp writes a row: coalesced, no index division
+                for (int l = lane; l < (int)lc; l += 32) out[(int64_t)r * lc + l] = tile[r * ldt + l];
             __syncthreads();
         }
     }
@@ -233,20 +230,44 @@ __device__ __forceinline__ void block_max_nan(double d, bool isn, unsigned long 
 __global__ void k_source_update(int64_t n, int64_t nlam, const double* __restrict__ lam, const double* __restrict__ T,
                                 const double* __restrict__ B0, const double* __restrict__ eps, const double* __restrict__ J,
                                 double* __restrict__ S, int use_thick, unsigned long long* diff_bits, int* diff_nan) {
-    int64_t total = n * nlam;
     double dmax = 0.0;
     bool isn = false;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        int64_t c = i / nlam, l = i - c * nlam;
-        double e = eps[c];
-        double B = B0 ? B0[c] : B_lambda(lam[l], T[c]);
-        double s_old = S[i];
-        double s_new = (1 - e) * J[i] + e * B;
-        S[i] = s_new;
-        if (!use_thick || e > 1e-4) {
-            double d = fabs(1 - s_old / s_new);
-            if (d != d) isn = true;
-            else dmax = fmax(dmax, d);
+    if (nlam < 16) {   // narrow rows (continuum: one wavelength): flat over the elements
+        const int64_t total = n * nlam;
+        for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+            const int64_t c = i / nlam, l = i - c * nlam;
+            const double e = eps[c];
+            const double B = B0 ? B0[c] : B_lambda(lam[l], T[c]);
+            const double s_old = S[i];
+            const double s_new = (1 - e) * J[i] + e * B;
+            S[i] = s_new;
+            if (!use_thick || e > 1e-4) {
+                const double d = fabs(1 - s_old / s_new);
+                if (d != d) isn = true;
+                else dmax = fmax(dmax, d);
+            }
+        }
+        block_max_nan(dmax, isn, diff_bits, diff_nan);
+        return;
+    }
+    // a warp per cell row (wavelengths across the lanes): no 64-bit index division per element, ε and T read once per row
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t c = warp; c < n; c += nwarps) {
+        const double e = eps[c];
+        const double Tc = B0 ? 0.0 : T[c];
+        const bool counts = !use_thick || e > 1e-4;
+        for (int64_t l = lane; l < nlam; l += 32) {
+            const int64_t i = c * nlam + l;
+            const double B = B0 ? B0[c] : B_lambda(lam[l], Tc);
+            const double s_old = S[i];
+            const double s_new = (1 - e) * J[i] + e * B;
+            S[i] = s_new;
+            if (counts) {
+                const double d = fabs(1 - s_old / s_new);
+                if (d != d) isn = true;
+                else dmax = fmax(dmax, d);
+            }
         }
     }
     block_max_nan(dmax, isn, diff_bits, diff_nan);
@@ -1452,7 +1473,7 @@ int vrt_lambda_iterate(vrt_solver* s, double eps, int32_t maxiter, vrt_iter_cb c
                                                                        c0 * s->nlam, s->J.p + c0 * s->nlam, s->S.p + c0 * s->nlam,
                                                                        s->diff_bits.p, s->diff_nan.p);
         } else if (cn > 0)
-            k_source_update<<<nblocks(cn * s->nlam, 256), 256>>>(cn, s->nlam, s->lam_dev.p + s->l_begin, s->T.p + c0,
+            k_source_update<<<std::min(nblocks(cn * s->nlam, 256), 148 * 64), 256>>>(cn, s->nlam, s->lam_dev.p + s->l_begin, s->T.p + c0,
                                                                  s->is_line ? nullptr : s->B0.p + c0, s->eps.p + c0, s->J.p + c0 * s->nlam,
                                                                  s->S.p + c0 * s->nlam, use_thick, s->diff_bits.p, s->diff_nan.p);
         VRT_CUDA(cudaEventRecord(e[1]));
