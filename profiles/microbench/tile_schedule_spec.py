@@ -29,7 +29,10 @@ alpha = 10.0 ** rng.uniform(-8, -4, n)
 NS = 3
 
 
-def run(theta, phi, cells_per_tile=64):
+def run(theta, phi, cells_per_tile=64, blocks=None, slab=0):
+    """blocks = (bx, by), slab = levels per slab: the key of schedule.cu rule 5 (round 2) instead of the tile key:
+    key = (slab of the visit's level, rank of its column block in upwind order, level), pushed behind the producers by
+    key(v) = max(base(v), key(p) + 1) on the level field — equal keys are then mutually independent visits."""
     t, p = theta * np.pi / 180, phi * np.pi / 180
     k = np.array([np.cos(t), np.cos(p) * np.sin(t), np.sin(p) * np.sin(t)])
     down = int(theta < 90)
@@ -80,6 +83,48 @@ def run(theta, phi, cells_per_tile=64):
         d = [op[1:] for op in (operand(c, 0, s), operand(c, 1, s)) if op[0] == "visit"]
         deps[(c, s)] = d
         level[(c, s)] = 1 + max([level[x] for x in d], default=0)
+    if blocks is not None:
+        bx, by = blocks
+        ix = np.clip(((pos[1] - b[2]) / (b[3] - b[2]) * bx).astype(np.int64), 0, bx - 1)
+        iy = np.clip(((pos[2] - b[4]) / (b[5] - b[4]) * by).astype(np.int64), 0, by - 1)
+        cx = b[2] + (np.arange(bx) + 0.5) * (b[3] - b[2]) / bx
+        cy = b[4] + (np.arange(by) + 0.5) * (b[5] - b[4]) / by
+        proj = -(k[1] * cx[:, None] + k[2] * cy[None, :]).ravel()
+        rank = np.empty(bx * by, dtype=np.int64)
+        rank[np.argsort(proj, kind="stable")] = np.arange(bx * by)
+        brank = rank[ix * by + iy]
+        key = {}
+        pushed = 0
+        for v in order_ref:                      # producers first: one pass reaches the least fixed point
+            lv = level[v]
+            kk = ((lv - 1) // slab if slab > 0 else 0, int(brank[v[0]]), lv)
+            for x in deps[v]:
+                kx = key[x]
+                cand = (kx[0], kx[1], kx[2] + 1)
+                if cand > kk:
+                    kk = cand
+                    pushed += 1
+            key[v] = kk
+        # equal keys never depend on each other, and every producer has a smaller key
+        assert all(key[x] < key[v] for v in order_ref for x in deps[v])
+        order = sorted(order_ref, key=lambda v: (key[v], proc[v[0]], v[1]))
+        val = {}
+        for (c, s) in order:
+            acc = 0.0
+            for m in (0, 1):
+                op = operand(c, m, s)
+                Iu = final0[op[1]] if op[0] == "fixed" else (0.0 if op[0] == "zero" else val[(op[1], op[2])])
+                v_ = u[c, m]
+                a, bb, e = linear_weights(r[c, m] * (alpha[c] + alpha[v_]) / 2)
+                acc += (e * Iu + a * S[v_] + bb * S[c]) * w[c, m]
+            val[(c, s)] = acc
+        out = final0.copy()
+        for c in processed:
+            out[c] = val[(c, NS)]
+        same = np.array_equal(out, ref)
+        print(f"theta {theta:6.1f} phi {phi:6.1f}: blocks {bx}x{by}, slab {slab}: {len(order)} visits, {len(set(key.values()))} distinct keys, "
+              f"{pushed} pushes, blocked execution == sequential oracle bit for bit: {same}")
+        return same
     # tile key, pushed behind the producers
     ntile = max(1, int(round((n / cells_per_tile) ** (1 / 3))))
     qq = ((pos - pos.min(axis=1, keepdims=True)) / (np.ptp(pos, axis=1)[:, None] + 1e-300) * ntile).astype(np.int64).clip(0, ntile - 1)

@@ -445,3 +445,22 @@ def test_direction_split_by_wavelength_adds_up(V, oracle):
     b.close()
     assert not Jb[:half].any()                               # nothing outside the assigned wavelengths
     assert rel_err(Ja + Jb, Jref) < 1e-13
+
+
+def test_blocked_visit_order_is_bit_identical(V, oracle, monkeypatch):
+    """schedule.cu rule 5 (VRT_BLOCKS / VRT_SLAB): another topological order of the same visits, so not one bit of J moves"""
+    from voronoirt_b200 import atom
+    P = line_problem(V, oracle, "grid_strat3000", nbb=10, nbf=4)
+    line, sites = P["line"], P["sites"]
+    qp = V.quadrature_path("ul7n12")
+    S = np.asfortranarray(atom.B_λ(line.λ[:, None], sites.temperature[None, :]))
+    a = V.Solver(sites, qp, line=line, α_cont=P["α_cont"], LTE_pops=P["lte"])
+    Ja = a.mean_intensity(S, P["lte"])
+    a.close()
+    monkeypatch.setenv("VRT_BLOCKS", "3,2")
+    monkeypatch.setenv("VRT_SLAB", "5")
+    monkeypatch.setenv("VRT_STEP_MIN", "64")
+    b = V.Solver(sites, qp, line=line, α_cont=P["α_cont"], LTE_pops=P["lte"])
+    Jb = b.mean_intensity(S, P["lte"])
+    b.close()
+    assert np.array_equal(Ja, Jb)
