@@ -585,6 +585,9 @@ def main():
                "stage_ms": {k: float(np.mean([h[k] for h in hist])) for k in ("t_opacity_ms", "t_sweep_ms", "t_source_ms", "t_rates_ms", "t_stateq_ms", "t_total_ms")} if hist else None}
         print(json.dumps(out))
     if solver is not None:
+        if dist is not None:      # importers unmap the peers' J buffers before any exporter frees its own
+            solver.peer_detach()
+            dist.barrier()
         solver.close()
     if dist is not None:
         dist.destroy_process_group()

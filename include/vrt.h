@@ -317,6 +317,9 @@ int vrt_solver_direction_visits(const vrt_solver* s, int64_t* n_dirs, double* vi
  * using the reduce-scatter. */
 int vrt_solver_peer_handle(vrt_solver* s, char handle[64]);
 int vrt_solver_peer_attach(vrt_solver* s, const char* handles, int32_t count);
+/* Unmaps the peers' buffers (the solver goes back to the reduce-scatter).  CUDA requires that every importer has closed a handle
+ * before the exporter frees the memory: call this on every process, then synchronise the processes, then destroy the solvers. */
+int vrt_solver_peer_detach(vrt_solver* s);
 
 /* Restricts one direction of this solver (index into its quadrature table without the θ = 90 rows) to the local wavelengths
  * [lam_begin, lam_end): the direction is then shared with another process that takes the remaining wavelengths (both add

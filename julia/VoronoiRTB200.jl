@@ -271,6 +271,7 @@ function peer_handle(solver::Ptr{Cvoid})
 end
 peer_attach!(solver::Ptr{Cvoid}, handles::Vector{UInt8}) =
     check(ccall((:vrt_solver_peer_attach, libvrt), Cint, (Ptr{Cvoid}, Ptr{UInt8}, Int32), solver, handles, length(handles) ÷ 64))
+peer_detach!(solver::Ptr{Cvoid}) = check(ccall((:vrt_solver_peer_detach, libvrt), Cint, (Ptr{Cvoid},), solver))   # all ranks, then a barrier, then destroy
 # direction `d` (0-based index in the solver's own table) on the local wavelengths [lo, hi) only: a direction shared with another
 # process that takes the rest (20 directions on 8 GPUs: two whole directions and half of a ninth each)
 set_direction_lambda!(solver::Ptr{Cvoid}, d::Integer, lo::Integer, hi::Integer) =

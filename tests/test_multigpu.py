@@ -130,6 +130,7 @@ def _worker(rank, world, port, q, mode):
     out = dict(S=S, J=J, pops=pops, diffs=[h["diff"] for h in res["history"]] + [h["diff"] for h in res2["history"]], slice=(c0, c1),
                checksum=chk, S_slice=Ss)
     q.put((rank, out))
+    s.peer_detach()          # (no-op unless peers were attached) importers first, then a barrier, then the solvers go
     dist.barrier()
     s.close()
     dist.destroy_process_group()

@@ -124,6 +124,7 @@ PROTOTYPES = {
     "vrt_solver_comm_init": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int32, C.c_int32, C.c_char_p, C.c_int32, C.c_int32]),
     "vrt_solver_peer_handle": (C.c_int, [C.c_void_p, C.c_char_p]),
     "vrt_solver_peer_attach": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int32]),
+    "vrt_solver_peer_detach": (C.c_int, [C.c_void_p]),
     "vrt_solver_set_direction_lambda": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_int64]),
     "vrt_solver_direction_visits": (C.c_int, [C.c_void_p, c_int64_p, c_double_p, C.c_int64]),
     "vrt_solver_cell_slice": (C.c_int, [C.c_void_p, c_int64_p, c_int64_p]),

@@ -603,6 +603,10 @@ class Solver:
         """handles of the whole direction group in rank order (bytes, 64 per rank): J is then reduced through peer memory"""
         check(lib().vrt_solver_peer_attach(self.h, handles, len(handles) // 64))
 
+    def peer_detach(self):
+        """unmap the peers' J buffers; every process must do this (then synchronise) before any of them closes its solver"""
+        check(lib().vrt_solver_peer_detach(self.h))
+
     def cell_slice(self):
         """[first, last) of the cells this process owns, in internal order (site perm_up[c])"""
         a, b = C.c_int64(), C.c_int64()

@@ -1710,6 +1710,18 @@ int vrt_solver_peer_attach(vrt_solver* s, const char* handles, int32_t count) {
     return VRT_OK;
 }
 
+int vrt_solver_peer_detach(vrt_solver* s) {
+    if (!s) return VRT_E_INVALID;
+    if (!s->peers) return VRT_OK;
+    VRT_CUDA(cudaDeviceSynchronize());
+    for (int r = 0; r < 16; r++) {
+        if (s->peerJ[r] && r != s->cell_r) cudaIpcCloseMemHandle(const_cast<double*>(s->peerJ[r]));
+        s->peerJ[r] = nullptr;
+    }
+    s->peers = false;
+    return VRT_OK;
+}
+
 int vrt_solver_set_direction_lambda(vrt_solver* s, int32_t direction, int64_t lam_begin, int64_t lam_end) {
     if (!s) return VRT_E_INVALID;
     if (s->g->regular || !s->is_line) {
