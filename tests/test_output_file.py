@@ -124,3 +124,22 @@ def test_write_state_from_the_device(tmp_path):
     assert np.array_equal(f["positions"].read(), pos.T)
     assert np.array_equal(f["convergence"].read()[:2], np.array(diffs))
     assert np.array_equal(f["wavelength"].read(), line.λ)
+
+
+def test_messages_are_byte_identical_to_what_libhdf5_writes(tmp_path):
+    """the datatype and fill-value messages of a Float64 dataset, byte for byte, against the same messages in the file written by
+    the HDF5 library; dataspace and symbol-table structures of both files pass the same parser (above)"""
+    from voronoirt_b200 import api
+    path = tmp_path / "m.h5"
+    api.create_output_file(path, 3, 5, 2).close()
+    ours, real = H.File(str(path)), H.File(os.path.join(GOLDEN, "libhdf5_sample.mat"))
+
+    def messages(f, name):
+        return {t: (fl, bytes(d)) for t, fl, d in H._messages(f, f.root.entries[name][0])}
+    a, b = messages(ours, "temperature"), messages(real, "testdouble")
+    assert a[0x0003] == b[0x0003]                 # IEEE binary64 little-endian datatype, flags included
+    assert a[0x0005] == b[0x0005]                 # fill value message (version 1: late allocation, written if set, default value)
+    assert a[0x0001][1][:8] == bytes([1, 1, 0, 0, 0, 0, 0, 0]) and b[0x0001][1][:8] == bytes([1, 2, 0, 0, 0, 0, 0, 0])   # dataspace v1, rank 1 / 2
+    # superblock fields other than addresses and K values
+    so, sr = ours.buf[:16], real.buf[512:528]
+    assert so == sr
