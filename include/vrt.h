@@ -369,7 +369,7 @@ int vrt_set_state_slice(vrt_solver* s, const double* S, const double* population
 /* ---------------------------------------------------------------- output / checkpoint file
  * create_output_file + write_to_file (io.jl:57-225) without the HDF5 library: a version-0-superblock HDF5 file with one flat
  * root group of contiguous little-endian datasets carrying the reference's names and shapes, so that
- * recover_simulation.jl:213-277 and python/*.py read it like a file written by HDF5.jl.  Dataset names (Voronoi,
+ * recover_simulation.jl:213-277 and the scripts under python/ read it like a file written by HDF5.jl.  Dataset names (Voronoi,
  * io.jl:196-225): source_function (nλ, n_sites), populations (n_sites, 3), positions (3, n_sites), temperature,
  * hydrogen_populations, electron_density, velocity_z, velocity_x, velocity_y (n_sites), boundaries (6), convergence
  * (maxiter+1, created as zeros), n_bb, n_bf (1, Int64), wavelength (nλ), line_center (1), time (1); the regular-grid form

@@ -195,3 +195,20 @@ def test_wavelength_sharding_with_two_gloo_ranks():
         p.join(timeout=60)
     same, rdiff, dmax, jmax = res
     assert same and rdiff == 0.0 and dmax == jmax
+
+
+def test_c_host_example_compiles_and_links_against_the_library(tmp_path):
+    """examples/lambda_checkpoint.c (a C host with the per-iteration checkpoint callback) is valid C against include/vrt.h and
+    resolves every symbol it uses in libvrt.so (compile + link only: running it needs a device)"""
+    from voronoirt_b200 import _lib
+    gcc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
+    obj = tmp_path / "ex.o"
+    subprocess.run([gcc, "-std=c11", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), "-c", os.path.join(ROOT, "examples", "lambda_checkpoint.c"),
+                    "-o", str(obj)], check=True)
+    main = tmp_path / "main.c"
+    main.write_text('#include "vrt.h"\nint run_lambda(const char*, int64_t, const double*, const double*, const vrt_line*, const double*, const vrt_site_data*, '
+                    'const vrt_quadrature*, const char*);\nint main(void){ return vrt_abi_version() == VRT_ABI_VERSION && (void*)run_lambda != 0 ? 0 : 1; }\n')
+    exe = tmp_path / "ex"
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    subprocess.run([gcc, "-I", os.path.join(ROOT, "include"), str(main), str(obj), "-L", libdir, "-lvrt", f"-Wl,-rpath,{libdir}", "-o", str(exe)], check=True)
+    assert subprocess.run([str(exe)]).returncode == 0      # loads libvrt.so, the ABI version matches the header
